@@ -1,0 +1,179 @@
+"""ctypes binding of the CPU parity oracle (oracle/libref_arpack.so). Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "libref_arpack.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+c_flt_p = C.POINTER(C.c_float)
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.ref_ctx_new.restype = C.c_void_p
+        L.ref_ctx_free.argtypes = [C.c_void_p]
+        L.ref_ctx_set_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]
+        L.ref_ctx_stats.argtypes = [C.c_void_p] + [c_int_p] * 5
+        for p, rp, rt in (("d", c_dbl_p, C.c_double), ("s", c_flt_p, C.c_float)):
+            for fam in ("s", "n"):
+                if not hasattr(L, f"ref_{p}{fam}aupd"):
+                    continue
+                f = getattr(L, f"ref_{p}{fam}aupd")
+                f.argtypes = [C.c_void_p, c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rp, rp, C.c_int, rp,
+                              C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+                f.restype = None
+            f = getattr(L, f"ref_{p}seupd")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, rp, rp, C.c_int, rt, C.c_char_p, C.c_int,
+                          C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+            f.restype = None
+            if not hasattr(L, f"ref_{p}neupd"):
+                continue
+            f = getattr(L, f"ref_{p}neupd")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, rp, rp, rp, C.c_int, rt, rt, rp, C.c_char_p,
+                          C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
+                          C.c_int, c_int_p]
+            f.restype = None
+        L.ref_dlarnv2.argtypes = [c_int_p, C.c_int, c_dbl_p]
+        L.ref_csr_spmv.argtypes = [C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int]
+        L.ref_set_blas_threads.argtypes = [C.c_int]
+        L.ref_get_blas_threads.restype = C.c_int
+        L.ref_dsaupd_csr_solve.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p, C.c_char_p, C.c_int,
+                                           C.c_int, C.c_double, C.c_int, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+                                           c_dbl_p, c_int_p, C.c_int, c_dbl_p, c_dbl_p]
+        L.ref_dsaupd_csr_solve.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Result(dict):
+    __getattr__ = dict.__getitem__
+
+
+class Oracle:
+    """One 'process' of the reference: SAVE'd state (e.g. the dgetv0 seed) persists across solves."""
+
+    def __init__(self, rank=None, nranks=None, allreduce=None):
+        self.L = lib()
+        self.ctx = C.c_void_p(self.L.ref_ctx_new())
+        self._cb = None
+        if rank is not None:
+            def _ar(user, buf, count, is_double, op):
+                dt = np.float64 if is_double else np.float32
+                arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double if is_double else C.c_float)), (count,))
+                arr[:] = allreduce(arr.astype(dt), op)
+            self._cb = ALLREDUCE_FN(_ar)
+            self.L.ref_ctx_set_comm(self.ctx, rank, nranks, self._cb, None)
+
+    def __del__(self):
+        try:
+            self.L.ref_ctx_free(self.ctx)
+        except Exception:
+            pass
+
+    def stats(self):
+        v = [C.c_int() for _ in range(5)]
+        self.L.ref_ctx_stats(self.ctx, *[C.byref(x) for x in v])
+        return dict(zip(("nopx", "nbx", "nrorth", "nitref", "nrstrt"), [x.value for x in v]))
+
+    def solve(self, op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
+              dtype=np.float64, bop=None, rvec=True, sigma=0.0, sigmai=0.0, c_abi_tol=False, ishift=1,
+              eupd=True, ldv=None):
+        """RCI loop exactly as EXAMPLES/SIMPLE/dssimp.f:302-324 drives it.
+        op(x)->y, bop(x)->y.  c_abi_tol=True mimics the *_c entry points (tol by value, see SRC/icbads.F90)."""
+        L = self.L
+        dt = np.dtype(dtype)
+        p = "d" if dt == np.float64 else "s"
+        rp = c_dbl_p if p == "d" else c_flt_p
+        rt = C.c_double if p == "d" else C.c_float
+        fam = "s" if sym else "n"
+        ldv = ldv or n
+        lworkl = ncv * ncv + 8 * ncv if sym else 3 * ncv * ncv + 6 * ncv
+        v = np.zeros((ncv, ldv), dtype=dt)  # column-major (ldv, ncv)
+        workd = np.zeros(3 * n, dtype=dt)
+        workl = np.zeros(lworkl, dtype=dt)
+        iparam = np.zeros(11, dtype=np.int32)
+        ipntr = np.zeros(14, dtype=np.int32)
+        iparam[0] = ishift
+        iparam[2] = mxiter
+        iparam[3] = 1
+        iparam[6] = mode
+        info = C.c_int(0)
+        if resid is None:
+            res = np.zeros(n, dtype=dt)
+        else:
+            res = np.array(resid, dtype=dt).copy()
+            info.value = 1
+        ido = C.c_int(0)
+        tolv = rt(tol)
+        aupd = getattr(L, f"ref_{p}{fam}aupd")
+        nsteps = 0
+        while True:
+            if c_abi_tol:
+                tolv = rt(tol)
+            aupd(self.ctx, C.byref(ido), bmat.encode(), n, which.encode(), nev, C.byref(tolv), _p(res, rp), ncv,
+                 _p(v, rp), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl,
+                 C.byref(info))
+            if ido.value in (-1, 1):
+                x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
+                if mode == 2 and ido.value == 1:
+                    y, ax = op(x)  # mode 2: op returns (M^-1 A x, A x); x is overwritten with A x
+                    workd[ipntr[0] - 1: ipntr[0] - 1 + n] = ax
+                    workd[ipntr[1] - 1: ipntr[1] - 1 + n] = y
+                elif mode >= 3 and ido.value == 1 and bmat == "G":
+                    workd[ipntr[1] - 1: ipntr[1] - 1 + n] = op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], True)
+                else:
+                    r = op(x)
+                    workd[ipntr[1] - 1: ipntr[1] - 1 + n] = r[0] if isinstance(r, tuple) else r
+                nsteps += 1
+            elif ido.value == 2:
+                workd[ipntr[1] - 1: ipntr[1] - 1 + n] = bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n])
+            else:
+                break
+        out = Result(info=info.value, iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v.copy(),
+                     resid=res.copy(), nconv=int(iparam[4]), stats=self.stats(), tol_eff=tolv.value)
+        if info.value < 0 or not eupd:
+            return out
+        select = np.zeros(ncv, dtype=np.int32)
+        ierr = C.c_int(0)
+        tol_e = tol if c_abi_tol else tolv.value
+        if sym:
+            d = np.zeros(nev, dtype=dt)
+            z = np.zeros((nev, n), dtype=dt)
+            L_ = getattr(L, f"ref_{p}seupd")
+            L_(self.ctx, int(rvec), b"A", _p(select, c_int_p), _p(d, rp), _p(z, rp), n, rt(sigma), bmat.encode(), n,
+               which.encode(), nev, rt(tol_e), _p(res, rp), ncv, _p(v, rp), ldv, _p(iparam, c_int_p),
+               _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl, C.byref(ierr))
+            out.update(d=d, z=z, ierr=ierr.value)
+        else:
+            dr = np.zeros(nev + 1, dtype=dt)
+            di = np.zeros(nev + 1, dtype=dt)
+            z = np.zeros((nev + 1, n), dtype=dt)
+            workev = np.zeros(3 * ncv, dtype=dt)
+            L_ = getattr(L, f"ref_{p}neupd")
+            L_(self.ctx, int(rvec), b"A", _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
+               rt(sigmai), _p(workev, rp), bmat.encode(), n, which.encode(), nev, rt(tol_e), _p(res, rp), ncv,
+               _p(v, rp), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl,
+               C.byref(ierr))
+            out.update(dr=dr, di=di, z=z, ierr=ierr.value)
+        out.update(workl_eupd=workl.copy(), v_eupd=v.copy(), ipntr_eupd=ipntr.copy(), select=select.copy())
+        return out
