@@ -167,7 +167,7 @@ class Oracle:
         else:
             dr = np.zeros(nev + 1, dtype=dt)
             di = np.zeros(nev + 1, dtype=dt)
-            z = np.zeros((nev + 1, n), dtype=dt)
+            z = np.zeros((max(ncv, nev + 1), n), dtype=dt)  # dneupd.f:893 treats Z as n x ncv
             workev = np.zeros(3 * ncv, dtype=dt)
             L_ = getattr(L, f"ref_{p}neupd")
             L_(self.ctx, int(rvec), b"A", _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
