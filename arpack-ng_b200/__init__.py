@@ -1,0 +1,422 @@
+"""arpack-ng_b200 -- Python host-side mirror of the reference's reverse-communication interface.
+
+The product is the C-ABI shared library ``arpack-ng_b200/lib/libarpack_b200.so`` (sm_100a CUDA kernels +
+C++ host control; see ``include/arpack_b200.h``).  This module is the thin ctypes binding a Python caller
+uses, with the same entry-point names and argument meaning as ``ICB/arpack.h`` / ``ICB/parpack.h`` of
+arpack-ng (``dsaupd_c``, ``dseupd_c``, ``dnaupd_c``, ``dneupd_c``, ``pdsaupd_c`` ...), plus an
+``arpackmm``-style convenience driver (``eigsh_csr``; EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:721-880).
+
+PyTorch is used only for device memory, streams and (multi-GPU) torch.distributed plumbing.
+There is no CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
+
+The directory name contains a hyphen; import it through the ``arpack_ng_b200`` shim at the repo root.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libarpack_b200.so")
+
+c_int_p = C.POINTER(C.c_int)
+_lib = None
+
+INFO_DEVICE_ERROR = -9990
+
+
+class ArpackB200Error(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libarpack_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    import subprocess
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise ArpackB200Error("building libarpack_b200.so failed")
+    return LIB_PATH
+
+
+def _sig_aupd(rp, rt, par):
+    a = [c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
+         C.c_int, c_int_p]
+    return ([C.c_int] if par else []) + a
+
+
+def _sig_seupd(rp, rt, par):
+    a = [C.c_int, C.c_char_p, c_int_p, rp, rp, C.c_int, rt, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int,
+         rp, C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+    return ([C.c_int] if par else []) + a
+
+
+def _sig_neupd(rp, rt, par):
+    a = [C.c_int, C.c_char_p, c_int_p, rp, rp, rp, C.c_int, rt, rt, rp, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rt,
+         rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+    return ([C.c_int] if par else []) + a
+
+
+def lib():
+    """Load the C-ABI library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ArpackB200Error(f"{LIB_PATH} not found: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU path.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp = C.c_void_p  # array arguments are passed as raw addresses (host or device)
+    for p, rt in (("d", C.c_double), ("s", C.c_float)):
+        for par in (False, True):
+            pre = "p" if par else ""
+            for fam in ("s", "n"):
+                f = getattr(L, f"{pre}{p}{fam}aupd_c")
+                f.argtypes = _sig_aupd(vp, rt, par)
+                f.restype = None
+            f = getattr(L, f"{pre}{p}seupd_c")
+            f.argtypes = _sig_seupd(vp, rt, par)
+            f.restype = None
+            f = getattr(L, f"{pre}{p}neupd_c")
+            f.argtypes = _sig_neupd(vp, rt, par)
+            f.restype = None
+    L.ab200_set_stream.argtypes = [vp]
+    L.ab200_get_stream.restype = vp
+    L.ab200_set_kernel_mode.argtypes = [C.c_int]
+    L.ab200_release.argtypes = [vp]
+    L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
+    L.ab200_device_count.restype = C.c_int
+    L.ab200_version.restype = C.c_char_p
+    L.ab200_nccl_unique_id.argtypes = [vp]
+    L.ab200_comm_create.argtypes = [vp, C.c_int, C.c_int]
+    L.ab200_comm_destroy.argtypes = [C.c_int]
+    L.ab200_csr_spmv_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+    L.ab200_csr_spmv_f32.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+    L.ab200_csr_spmv_hostvec_f64.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.ab200_csr_spmv_halo_f64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.ab200_gen_laplace2d.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, vp]
+    L.ab200_gen_laplace2d.restype = C.c_longlong
+    L.ab200_gen_laplace3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.ab200_gen_laplace3d.restype = C.c_longlong
+    L.ab200_gen_convdiff2d.argtypes = [C.c_int, C.c_double, vp, vp, vp]
+    L.ab200_gen_convdiff2d.restype = C.c_longlong
+    L.ab200_fill_hash_f64.argtypes = [C.c_longlong, C.c_longlong, C.c_ulonglong, vp]
+    L.ab200_residuals_f64.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.c_longlong, vp, vp]
+    _lib = L
+    return L
+
+
+def launch_stats():
+    out = (C.c_ulonglong * 4)()
+    lib().ab200_launch_stats(out)
+    return {"kernels": int(out[0]), "allreduces": int(out[1]), "tma_path": int(out[2]), "generic_path": int(out[3])}
+
+
+def _addr(a):
+    """Raw address of a numpy array (host) or a torch tensor (host or device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _real(dtype):
+    dt = np.dtype(dtype) if not hasattr(dtype, "is_floating_point") else None
+    if dt is None:
+        import torch
+        return ("d", C.c_double) if dtype == torch.float64 else ("s", C.c_float)
+    return ("d", C.c_double) if dt == np.float64 else ("s", C.c_float)
+
+
+def _prec_of(arr):
+    if isinstance(arr, np.ndarray):
+        return ("d", C.c_double) if arr.dtype == np.float64 else ("s", C.c_float)
+    return _real(arr.dtype)
+
+
+# ---- the reference's entry points (ICB/arpack.h); ido/info are 1-element int32 numpy arrays -------
+def _call_aupd(name, comm, ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, info):
+    p, rt = _prec_of(workl)
+    f = getattr(lib(), f"{'p' if comm is not None else ''}{p}{name}_c")
+    args = [ido.ctypes.data_as(c_int_p), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(resid), ncv, _addr(v),
+            ldv, iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl),
+            int(workl.size), info.ctypes.data_as(c_int_p)]
+    if comm is not None:
+        args = [comm] + args
+    f(*args)
+    if info[0] == INFO_DEVICE_ERROR:
+        raise ArpackB200Error(f"{name}_c: CUDA device error (see stderr); there is no CPU fallback")
+
+
+def dsaupd_c(ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, info, comm=None):
+    """SRC/icbads.F90:3-40 (dsaupd_c) / ssaupd_c by dtype of workl; comm != None -> pdsaupd_c."""
+    _call_aupd("saupd", comm, ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, info)
+
+
+def dnaupd_c(ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, info, comm=None):
+    """SRC/icbadn.F90 (dnaupd_c) / snaupd_c by dtype of workl; comm != None -> pdnaupd_c."""
+    _call_aupd("naupd", comm, ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, info)
+
+
+def dseupd_c(rvec, howmny, select, d, z, ldz, sigma, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr,
+             workd, workl, info, comm=None):
+    """SRC/icbads.F90:42-92 (dseupd_c)."""
+    p, rt = _prec_of(workl)
+    f = getattr(lib(), f"{'p' if comm is not None else ''}{p}seupd_c")
+    args = [int(rvec), howmny.encode(), select.ctypes.data_as(c_int_p), _addr(d), _addr(z), ldz, rt(sigma),
+            bmat.encode(), n, which.encode(), nev, rt(tol), _addr(resid), ncv, _addr(v), ldv,
+            iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), int(workl.size),
+            info.ctypes.data_as(c_int_p)]
+    if comm is not None:
+        args = [comm] + args
+    f(*args)
+    if info[0] == INFO_DEVICE_ERROR:
+        raise ArpackB200Error("seupd_c: CUDA device error (see stderr)")
+
+
+def dneupd_c(rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which, nev, tol, resid, ncv, v,
+             ldv, iparam, ipntr, workd, workl, info, comm=None):
+    """SRC/icbadn.F90 (dneupd_c)."""
+    p, rt = _prec_of(workl)
+    f = getattr(lib(), f"{'p' if comm is not None else ''}{p}neupd_c")
+    args = [int(rvec), howmny.encode(), select.ctypes.data_as(c_int_p), _addr(dr), _addr(di), _addr(z), ldz,
+            rt(sigmar), rt(sigmai), _addr(workev), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(resid), ncv,
+            _addr(v), ldv, iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl),
+            int(workl.size), info.ctypes.data_as(c_int_p)]
+    if comm is not None:
+        args = [comm] + args
+    f(*args)
+    if info[0] == INFO_DEVICE_ERROR:
+        raise ArpackB200Error("neupd_c: CUDA device error (see stderr)")
+
+
+# ---- RCI driver in the style of arpackSolver.hpp:721-880 -------------------------------------------
+class Result(dict):
+    __getattr__ = dict.__getitem__
+
+
+def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.float64,
+          bop=None, rvec=True, sigma=0.0, sigmai=0.0, device="cuda", host_buffers=False, comm=None, ishift=1,
+          eupd=True, pinned=True):
+    """Run a whole *aupd/*eupd solve through the C-ABI.
+
+    device arrays (default): resid/v/workd are torch CUDA tensors; ``op(x, y)`` receives tensor views of the
+    workd slots and must fill y on the library's stream (torch's current stream == legacy default stream).
+    host_buffers=True: resid/v/workd are (pinned) host arrays exactly as an unmodified reference caller would
+    own them; ``op(x, y)`` then receives numpy views.
+    """
+    import torch
+    L = lib()
+    np_dt = np.dtype(dtype)
+    t_dt = torch.float64 if np_dt == np.float64 else torch.float32
+    lworkl = ncv * ncv + 8 * ncv if sym else 3 * ncv * ncv + 6 * ncv
+    workl = np.zeros(lworkl, dtype=np_dt)
+    iparam = np.zeros(11, dtype=np.int32)
+    ipntr = np.zeros(14, dtype=np.int32)
+    iparam[0], iparam[2], iparam[3], iparam[6] = ishift, mxiter, 1, mode
+    ido = np.zeros(1, dtype=np.int32)
+    info = np.zeros(1, dtype=np.int32)
+    ldv = n
+    if host_buffers:
+        def _h(cnt):
+            t = torch.zeros(cnt, dtype=t_dt)
+            return t.pin_memory() if pinned else t
+        v_t, workd_t, resid_t = _h(ldv * ncv), _h(3 * n), _h(n)
+        v, workd, res = v_t.numpy(), workd_t.numpy(), resid_t.numpy()
+        if resid is not None:
+            res[:] = np.asarray(resid, dtype=np_dt)
+            info[0] = 1
+    else:
+        v = torch.zeros(ldv * ncv, dtype=t_dt, device=device)
+        workd = torch.zeros(3 * n, dtype=t_dt, device=device)
+        if resid is not None:
+            res = torch.as_tensor(resid, dtype=t_dt).to(device).contiguous().clone()
+            info[0] = 1
+        else:
+            res = torch.zeros(n, dtype=t_dt, device=device)
+    aupd = dsaupd_c if sym else dnaupd_c
+    nsteps = 0
+    while True:
+        aupd(ido, bmat, n, which, nev, tol, res, ncv, v, ldv, iparam, ipntr, workd, workl, info, comm=comm)
+        if ido[0] in (-1, 1):
+            x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
+            y = workd[ipntr[1] - 1: ipntr[1] - 1 + n]
+            if mode >= 3 and bmat == "G" and ido[0] == 1:
+                op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], y, True)
+            else:
+                op(x, y)
+            nsteps += 1
+        elif ido[0] == 2:
+            bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n], workd[ipntr[1] - 1: ipntr[1] - 1 + n])
+        else:
+            break
+    out = Result(info=int(info[0]), iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v, resid=res,
+                 nconv=int(iparam[4]), nsteps=nsteps, workd=workd)
+    if info[0] < 0 or not eupd:
+        return out
+    select = np.zeros(ncv, dtype=np.int32)
+    ierr = np.zeros(1, dtype=np.int32)
+    if sym:
+        d = np.zeros(nev, dtype=np_dt)
+        dseupd_c(rvec, "A", select, d, v, ldv, sigma, bmat, n, which, nev, tol, res, ncv, v, ldv, iparam, ipntr, workd,
+                 workl, ierr, comm=comm)
+        out.update(d=d, z=v, ierr=int(ierr[0]))
+    else:
+        dr = np.zeros(nev + 1, dtype=np_dt)
+        di = np.zeros(nev + 1, dtype=np_dt)
+        workev = np.zeros(3 * ncv, dtype=np_dt)
+        dneupd_c(rvec, "A", select, dr, di, v, ldv, sigma, sigmai, workev, bmat, n, which, nev, tol, res, ncv, v, ldv,
+                 iparam, ipntr, workd, workl, ierr, comm=comm)
+        out.update(dr=dr, di=di, z=v, ierr=int(ierr[0]))
+    out.update(workl_eupd=workl.copy(), ipntr_eupd=ipntr.copy())
+    L.ab200_release(workl.ctypes.data)
+    return out
+
+
+# ---- driver-side operators on the device ------------------------------------------------------------
+class CsrOperator:
+    """A CSR matrix resident in HBM with y = A x on the library's stream (K3)."""
+
+    def __init__(self, n, rowptr, col, val, ncols=None):
+        self.n, self.rowptr, self.col, self.val = n, rowptr, col, val
+        self.ncols = ncols or n
+        self.nnz = int(val.numel())
+
+    @staticmethod
+    def laplace2d(nx, ny=None, scale=1.0, device="cuda"):
+        import torch
+        ny = ny or nx
+        L = lib()
+        n = nx * ny
+        nnz = L.ab200_gen_laplace2d(nx, ny, scale, None, None, None)
+        if nnz < 0:
+            raise ArpackB200Error("laplace2d: nnz exceeds int32")
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+        col = torch.empty(nnz, dtype=torch.int32, device=device)
+        val = torch.empty(nnz, dtype=torch.float64, device=device)
+        if L.ab200_gen_laplace2d(nx, ny, scale, rowptr.data_ptr(), col.data_ptr(), val.data_ptr()) != nnz:
+            raise ArpackB200Error("laplace2d generator failed")
+        return CsrOperator(n, rowptr, col, val)
+
+    @staticmethod
+    def convdiff2d(nx, rho=100.0, device="cuda"):
+        import torch
+        L = lib()
+        n = nx * nx
+        nnz = L.ab200_gen_convdiff2d(nx, rho, None, None, None)
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+        col = torch.empty(nnz, dtype=torch.int32, device=device)
+        val = torch.empty(nnz, dtype=torch.float64, device=device)
+        if L.ab200_gen_convdiff2d(nx, rho, rowptr.data_ptr(), col.data_ptr(), val.data_ptr()) != nnz:
+            raise ArpackB200Error("convdiff2d generator failed")
+        return CsrOperator(n, rowptr, col, val)
+
+    @staticmethod
+    def laplace3d(nx, ny, nz, z0=0, nzloc=None, device="cuda"):
+        import torch
+        L = lib()
+        nzloc = nz if nzloc is None else nzloc
+        nloc = nx * ny * nzloc
+        nnz = L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, None, None, None)
+        if nnz < 0:
+            raise ArpackB200Error("laplace3d: nnz exceeds int32")
+        rowptr = torch.empty(nloc + 1, dtype=torch.int32, device=device)
+        col = torch.empty(nnz, dtype=torch.int32, device=device)
+        val = torch.empty(nnz, dtype=torch.float64, device=device)
+        if L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, rowptr.data_ptr(), col.data_ptr(), val.data_ptr()) != nnz:
+            raise ArpackB200Error("laplace3d generator failed")
+        op = CsrOperator(nloc, rowptr, col, val)
+        op.halo_lo = nx * ny if z0 > 0 else 0
+        op.halo_hi = nx * ny if z0 + nzloc < nz else 0
+        op.halo = torch.zeros(max(1, op.halo_lo + op.halo_hi), dtype=torch.float64, device=device)
+        return op
+
+    @staticmethod
+    def from_scipy(A, device="cuda"):
+        import torch
+        A = A.tocsr()
+        A.sort_indices()
+        return CsrOperator(A.shape[0], torch.as_tensor(A.indptr.astype(np.int32), device=device),
+                           torch.as_tensor(A.indices.astype(np.int32), device=device),
+                           torch.as_tensor(A.data.astype(np.float64), device=device), ncols=A.shape[1])
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.n, self.ncols))
+
+    def __call__(self, x, y, *_):
+        """y = A x; x, y device tensors (views of workd) or host numpy arrays (host-buffer RCI loop)."""
+        L = lib()
+        if isinstance(x, np.ndarray):
+            rc = L.ab200_csr_spmv_hostvec_f64(self.n, self.ncols, self.rowptr.data_ptr(), self.col.data_ptr(),
+                                              self.val.data_ptr(), x.ctypes.data, y.ctypes.data)
+        else:
+            rc = L.ab200_csr_spmv_f64(self.n, self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
+                                      x.data_ptr(), y.data_ptr())
+        if rc != 0:
+            raise ArpackB200Error(f"csr_spmv failed ({rc})")
+
+    def apply_halo(self, comm, x, y):
+        rc = lib().ab200_csr_spmv_halo_f64(comm, self.n, self.halo_lo, self.halo_hi, self.rowptr.data_ptr(),
+                                          self.col.data_ptr(), self.val.data_ptr(), x.data_ptr(), y.data_ptr(),
+                                          self.halo.data_ptr())
+        if rc != 0:
+            raise ArpackB200Error(f"csr_spmv_halo failed ({rc})")
+
+    def spmv_bytes(self, w=8):
+        """Algorithmic traffic of one product: nnz*(w+4) + (n+1)*4 + 2*n*w."""
+        return self.nnz * (w + 4) + (self.n + 1) * 4 + 2 * self.n * w
+
+    def residuals(self, d, z, ldz):
+        out = np.zeros(len(d), dtype=np.float64)
+        dd = np.ascontiguousarray(d, dtype=np.float64)
+        rc = lib().ab200_residuals_f64(self.n, self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), len(d),
+                                       z.data_ptr(), ldz, dd.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise ArpackB200Error("residuals failed")
+        return out
+
+
+def hashed_start_vector(n, i0=0, seed=0x5EED, device="cuda"):
+    """resid[i] = 2 u(i0+i) - 1, u = top 53 bits of splitmix64(seed + i) / 2^53."""
+    import torch
+    x = torch.empty(n, dtype=torch.float64, device=device)
+    if lib().ab200_fill_hash_f64(n, i0, seed, x.data_ptr()) != 0:
+        raise ArpackB200Error("fill_hash failed")
+    return x
+
+
+def hashed_start_vector_numpy(n, i0=0, seed=0x5EED):
+    """CPU twin of hashed_start_vector (same bits), for the oracle side of parity tests."""
+    with np.errstate(over="ignore"):
+        x = (np.arange(i0, i0 + n, dtype=np.uint64) + np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    u = (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return 2.0 * u - 1.0
+
+
+def nccl_comm_from_torch_distributed():
+    """Create the library's NCCL communicator for the current torch.distributed world (one rank per GPU).
+    torch.distributed is only the bootstrap (it ships the 128-byte unique id); the data path is the library's own
+    communicator, used for the fused length-(j+1) all-reduces and the halo exchange."""
+    import torch
+    import torch.distributed as dist
+    L = lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = np.zeros(128, dtype=np.uint8)
+    if rank == 0 and L.ab200_nccl_unique_id(buf.ctypes.data) != 0:
+        raise ArpackB200Error("ncclGetUniqueId failed")
+    t = torch.from_numpy(buf)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    buf = t.cpu().numpy()
+    h = L.ab200_comm_create(buf.ctypes.data, rank, world)
+    if h < 1:
+        raise ArpackB200Error(f"ab200_comm_create failed ({h})")
+    return h

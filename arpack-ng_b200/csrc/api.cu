@@ -1,0 +1,500 @@
+// api.cu -- the C-ABI of libarpack_b200.so (declared in include/arpack_b200.h).
+//
+// Exports the reference's ISO_C_BINDING entry points with unchanged signatures
+// (ICB/arpack.h:12-21, ICB/parpack.h:20-27, SRC/icbads.F90, SRC/icbadn.F90), the legacy Fortran-ABI
+// names, the debug/stat accessors (ICB/debug_c.h, ICB/stat_c.h) and a few extensions.
+//
+// resid, v, workd and z may be HOST or DEVICE pointers, classified per array with
+// cudaPointerGetAttributes at ido = 0:
+//   * device pointers are used in place; the ido=+-1/2 hand-off then passes device addresses
+//     workd + ipntr[k] - 1 to the caller's OP kernel, ordered on ab200_get_stream();
+//   * host pointers get a device mirror owned by the solve context; the operand handed to the user
+//     is copied D2H before returning and the user's result H2D on re-entry, V/resid are copied back
+//     at ido = 99.  An unmodified CPU caller therefore works as is.
+// workl, iparam, ipntr, select, d/dr/di and workev are always host memory.
+//
+// There is no CPU fallback: without a usable CUDA device every entry point reports info = -9990
+// and prints the reason on stderr.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/arpack_b200.h"
+#include "irl_nonsym.hpp"
+#include "irl_sym.hpp"
+#include "vecops_cuda.cuh"
+
+namespace ab200 {
+NcclComm* comm_from_handle(int handle);
+
+namespace {
+
+constexpr int kInfoDeviceError = -9990;
+
+cudaStream_t g_stream = 0;
+int g_kernel_mode = 0;
+std::mutex g_mu;
+
+// COMMON /debug/ (debug.h) and the counters of COMMON /timing/ (stat.h) of the last solve
+struct DebugLevels { int v[24]; };
+DebugLevels g_debug = {{6, -3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+Counters g_last_counters;
+
+template <typename T> struct Globals {
+  static SeedState seed;       // dgetv0's SAVE'd iseed (dgetv0.f:164)
+  static SeedState seed_par;   // pdgetv0's
+  static T smlnum_first;       // dnaitr/dnapps SAVE'd smlnum from the n of the first call
+};
+template <typename T> SeedState Globals<T>::seed;
+template <typename T> SeedState Globals<T>::seed_par;
+template <typename T> T Globals<T>::smlnum_first = T(-1);
+
+template <typename T>
+struct Ctx {
+  std::unique_ptr<CudaVecOps<T>> ops;
+  std::unique_ptr<IrlSym<T>> sym;
+  std::unique_ptr<IrlNonsym<T>> nonsym;
+  bool par = false;
+  int n = 0, ncv = 0, mode = 1;
+  char bmat = 'I';
+  // user arrays
+  T *resid_u = nullptr, *v_u = nullptr, *workd_u = nullptr;
+  int64_t ldv_u = 0;
+  bool resid_host = false, v_host = false, workd_host = false;
+  // device views (== user pointers when those are device memory)
+  T *resid_d = nullptr, *v_d = nullptr, *workd_d = nullptr;
+  int64_t ldv_d = 0;
+  T* z_mirror = nullptr;
+  int last_ido = 0;
+  int last_ipntr[3] = {0, 0, 0};
+  bool finished = false;
+
+  ~Ctx() {
+    if (ops) {
+      try { ops->sync(); } catch (...) {}
+      if (resid_host) ops->release(resid_d);
+      if (v_host) ops->release(v_d);
+      if (workd_host) ops->release(workd_d);
+      ops->release(z_mirror);
+    }
+  }
+};
+
+template <typename T>
+std::unordered_map<const void*, std::unique_ptr<Ctx<T>>>& table() {
+  static std::unordered_map<const void*, std::unique_ptr<Ctx<T>>> t;
+  return t;
+}
+
+void require_device() {
+  int cnt = 0;
+  const cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                    "); arpack_b200 has no CPU path");
+  }
+}
+
+template <typename T>
+Ctx<T>* make_ctx(const void* key, bool par, int comm_handle, int n, int ncv, T* resid, T* v, int ldv, T* workd,
+                 bool upload_all) {
+  require_device();
+  auto c = std::make_unique<Ctx<T>>();
+  NcclComm* comm = nullptr;
+  if (par) {
+    comm = comm_from_handle(comm_handle);
+    if (!comm) throw CudaError("p*aupd_c: comm is not a handle returned by ab200_comm_create()");
+  }
+  c->ops = std::make_unique<CudaVecOps<T>>(g_stream, comm);
+  c->ops->set_kernel_mode(g_kernel_mode);
+  c->par = par;
+  c->n = n;
+  c->ncv = ncv;
+  c->resid_u = resid; c->v_u = v; c->workd_u = workd; c->ldv_u = ldv;
+  c->resid_host = !c->ops->is_device_pointer(resid);
+  c->v_host = !c->ops->is_device_pointer(v);
+  c->workd_host = !c->ops->is_device_pointer(workd);
+  if (n > 0 && ncv > 0) {
+    c->resid_d = c->resid_host ? c->ops->alloc((size_t)n) : resid;
+    if (c->v_host) {
+      c->ldv_d = ((int64_t)n + 1) & ~int64_t(1);  // even leading dimension: 16-byte aligned columns
+      c->v_d = c->ops->alloc((size_t)c->ldv_d * ncv);
+    } else {
+      c->ldv_d = ldv;
+      c->v_d = v;
+    }
+    c->workd_d = c->workd_host ? c->ops->alloc((size_t)3 * n) : workd;
+    if (upload_all) {
+      if (c->resid_host) c->ops->upload(c->resid_d, resid, (size_t)n);
+      if (c->v_host) c->ops->upload2d(c->v_d, (size_t)c->ldv_d, v, (size_t)ldv, (size_t)n, (size_t)ncv);
+      if (c->workd_host) c->ops->upload(c->workd_d, workd, (size_t)3 * n);
+    }
+  }
+  Ctx<T>* raw = c.get();
+  std::lock_guard<std::mutex> lk(g_mu);
+  table<T>()[key] = std::move(c);
+  return raw;
+}
+
+template <typename T>
+Ctx<T>* find_ctx(const void* key) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = table<T>().find(key);
+  return it == table<T>().end() ? nullptr : it->second.get();
+}
+
+template <typename T>
+void report(const char* where, const std::exception& e) {
+  std::fprintf(stderr, "arpack_b200: %s: %s\n", where, e.what());
+}
+
+// ---- one reverse-communication call, symmetric or nonsymmetric -------------------------------
+template <typename T, bool SYM>
+void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, const char* which, int nev, T* tol,
+                T* resid, int ncv, T* v, int ldv, int* iparam, int* ipntr, T* workd, T* workl, int lworkl,
+                int* info) {
+  try {
+    Ctx<T>* c = nullptr;
+    if (*ido == 0) {
+      c = make_ctx<T>(workl, par, comm_handle, n, ncv, resid, v, ldv, workd, false);
+      c->bmat = bmat[0];
+      c->mode = iparam[6];
+      SeedState* seed = par ? &Globals<T>::seed_par : &Globals<T>::seed;
+      if (SYM) c->sym = std::make_unique<IrlSym<T>>(c->ops.get(), par, seed);
+      else c->nonsym = std::make_unique<IrlNonsym<T>>(c->ops.get(), par, seed, &Globals<T>::smlnum_first);
+      if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
+    } else {
+      c = find_ctx<T>(workl);
+      if (!c || c->finished) throw CudaError("*aupd_c re-entered with ido != 0 but no active solve is keyed to this workl");
+      // the user's result of the previous hand-off
+      if (c->workd_host && (c->last_ido == -1 || c->last_ido == 1 || c->last_ido == 2)) {
+        c->ops->upload(c->workd_d + c->last_ipntr[1] - 1, c->workd_u + c->last_ipntr[1] - 1, (size_t)c->n);
+        if (c->mode == 2 && c->last_ido == 1)  // mode 2: x was overwritten with A*x (dsaupd.f:309-313)
+          c->ops->upload(c->workd_d + c->last_ipntr[0] - 1, c->workd_u + c->last_ipntr[0] - 1, (size_t)c->n);
+      }
+    }
+    if (SYM)
+      c->sym->aupd(ido, bmat[0], n, which, nev, tol, c->resid_d, ncv, c->v_d, c->ldv_d, iparam, ipntr, c->workd_d,
+                   workl, lworkl, info);
+    else
+      c->nonsym->aupd(ido, bmat[0], n, which, nev, tol, c->resid_d, ncv, c->v_d, c->ldv_d, iparam, ipntr,
+                      c->workd_d, workl, lworkl, info);
+    c->last_ido = *ido;
+    c->last_ipntr[0] = ipntr[0]; c->last_ipntr[1] = ipntr[1]; c->last_ipntr[2] = ipntr[2];
+    if (*ido == -1 || *ido == 1 || *ido == 2) {
+      if (c->workd_host) {
+        c->ops->download(c->workd_u + ipntr[0] - 1, c->workd_d + ipntr[0] - 1, (size_t)c->n);
+        if (*ido == 1 && (c->mode >= 3 || c->bmat == 'G'))
+          c->ops->download(c->workd_u + ipntr[2] - 1, c->workd_d + ipntr[2] - 1, (size_t)c->n);
+        c->ops->sync();
+      }
+    } else if (*ido == 99) {
+      g_last_counters = SYM ? c->sym->counters() : c->nonsym->counters();
+      // argument errors return before anything was built; every other exit leaves V/resid meaningful
+      if (c->ops && c->n > 0 && (*info >= 0 || *info == -8 || *info == -9 || *info == -9999)) {
+        if (c->resid_host) c->ops->download(resid, c->resid_d, (size_t)c->n);
+        if (c->v_host) c->ops->download2d(v, (size_t)ldv, c->v_d, (size_t)c->ldv_d, (size_t)c->n, (size_t)c->ncv);
+        if (c->workd_host && c->bmat == 'G') c->ops->download(workd, c->workd_d, (size_t)3 * c->n);
+      }
+      c->ops->sync();
+      c->finished = true;
+    }
+  } catch (const std::exception& e) {
+    report<T>(SYM ? "[ds]saupd_c" : "[ds]naupd_c", e);
+    *info = kInfoDeviceError;
+    *ido = 99;
+  }
+}
+
+template <typename T>
+struct ZView {
+  T* dev = nullptr;
+  int64_t ld = 0;
+  bool host = false;
+};
+
+template <typename T>
+ZView<T> map_z(Ctx<T>* c, T* z, int ldz, int cols, bool rvec) {
+  ZView<T> zv;
+  if (!rvec) return zv;
+  if (z == c->v_u) {  // Z aliases V
+    zv.dev = c->v_d; zv.ld = c->ldv_d; zv.host = false;
+    return zv;
+  }
+  zv.host = !c->ops->is_device_pointer(z);
+  if (zv.host) {
+    zv.ld = ((int64_t)c->n + 1) & ~int64_t(1);
+    c->ops->release(c->z_mirror);
+    c->z_mirror = c->ops->alloc((size_t)zv.ld * cols);
+    zv.dev = c->z_mirror;
+  } else {
+    zv.dev = z; zv.ld = ldz;
+  }
+  return zv;
+}
+
+template <typename T>
+Ctx<T>* ctx_for_eupd(bool par, int comm_handle, int n, int ncv, T* resid, T* v, int ldv, T* workd, T* workl) {
+  Ctx<T>* c = find_ctx<T>(workl);
+  if (c && c->finished && c->v_u == v && c->n == n && c->ncv == ncv) return c;
+  // *eupd without a preceding *aupd in this process (or with other arrays): rebuild the device view
+  c = make_ctx<T>(workl, par, comm_handle, n, ncv, resid, v, ldv, workd, true);
+  c->finished = true;
+  return c;
+}
+
+template <typename T>
+void seupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const int* select, T* d, T* z, int ldz,
+                 T sigma, const char* bmat, int n, const char* which, int nev, T tol, T* resid, int ncv, T* v,
+                 int ldv, int* iparam, int* ipntr, T* workd, T* workl, int lworkl, int* info) {
+  try {
+    Ctx<T>* c = ctx_for_eupd<T>(par, comm_handle, n, ncv, resid, v, ldv, workd, workl);
+    if (!c->sym) c->sym = std::make_unique<IrlSym<T>>(c->ops.get(), par, par ? &Globals<T>::seed_par : &Globals<T>::seed);
+    c->sym->ensure_mailbox(ncv);
+    ZView<T> zv = map_z(c, z, ldz, nev, rvec != 0);
+    std::vector<int> sel(select, select + (ncv > 0 ? ncv : 0));
+    c->sym->eupd(rvec != 0, howmny[0], sel.data(), d, zv.dev, zv.ld, sigma, bmat[0], n, which, nev, tol,
+                 c->resid_d, ncv, c->v_d, c->ldv_d, iparam, ipntr, c->workd_d, workl, lworkl, info);
+    if (rvec && *info == 0) {
+      const int nconv = iparam[4];
+      if (zv.host && z != c->v_u) c->ops->download2d(z, (size_t)ldz, zv.dev, (size_t)zv.ld, (size_t)n, (size_t)nconv);
+      if (c->v_host) c->ops->download2d(v, (size_t)ldv, c->v_d, (size_t)c->ldv_d, (size_t)n, (size_t)ncv);
+    }
+    c->ops->sync();
+  } catch (const std::exception& e) {
+    report<T>("[ds]seupd_c", e);
+    *info = kInfoDeviceError;
+  }
+}
+
+template <typename T>
+void neupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const int* select, T* dr, T* di, T* z,
+                 int ldz, T sigmar, T sigmai, T* workev, const char* bmat, int n, const char* which, int nev,
+                 T tol, T* resid, int ncv, T* v, int ldv, int* iparam, int* ipntr, T* workd, T* workl,
+                 int lworkl, int* info) {
+  try {
+    Ctx<T>* c = ctx_for_eupd<T>(par, comm_handle, n, ncv, resid, v, ldv, workd, workl);
+    if (!c->nonsym)
+      c->nonsym = std::make_unique<IrlNonsym<T>>(c->ops.get(), par, par ? &Globals<T>::seed_par : &Globals<T>::seed,
+                                                 &Globals<T>::smlnum_first);
+    c->nonsym->ensure_mailbox(ncv);
+    ZView<T> zv = map_z(c, z, ldz, nev + 1, rvec != 0);
+    std::vector<int> sel(select, select + (ncv > 0 ? ncv : 0));
+    c->nonsym->eupd(rvec != 0, howmny[0], sel.data(), dr, di, zv.dev, zv.ld, sigmar, sigmai, workev, bmat[0], n,
+                    which, nev, tol, c->resid_d, ncv, c->v_d, c->ldv_d, iparam, ipntr, c->workd_d, workl, lworkl,
+                    info);
+    if (rvec && *info == 0) {
+      const int nconv = iparam[4];
+      if (zv.host && z != c->v_u)
+        c->ops->download2d(z, (size_t)ldz, zv.dev, (size_t)zv.ld, (size_t)n, (size_t)std::min(nconv, nev + 1));
+      if (c->v_host) c->ops->download2d(v, (size_t)ldv, c->v_d, (size_t)c->ldv_d, (size_t)n, (size_t)ncv);
+    }
+    c->ops->sync();
+  } catch (const std::exception& e) {
+    report<T>("[ds]neupd_c", e);
+    *info = kInfoDeviceError;
+  }
+}
+
+}  // namespace
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" {
+
+// ---- ICB/arpack.h ------------------------------------------------------------------------------
+void dsaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+              a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+              a_int lworkl, a_int* info) {
+  aupd_entry<double, true>(false, 0, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                           workl, lworkl, info);
+}
+void dseupd_c(a_int rvec, char const* howmny, a_int const* select, double* d, double* z, a_int ldz, double sigma,
+              char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid, a_int ncv,
+              double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int lworkl,
+              a_int* info) {
+  seupd_entry<double>(false, 0, rvec, howmny, select, d, z, ldz, sigma, bmat, n, which, nev, tol, resid, ncv, v,
+                      ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void dnaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+              a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+              a_int lworkl, a_int* info) {
+  aupd_entry<double, false>(false, 0, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                            workl, lworkl, info);
+}
+void dneupd_c(a_int rvec, char const* howmny, a_int const* select, double* dr, double* di, double* z, a_int ldz,
+              double sigmar, double sigmai, double* workev, char const* bmat, a_int n, char const* which,
+              a_int nev, double tol, double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr,
+              double* workd, double* workl, a_int lworkl, a_int* info) {
+  neupd_entry<double>(false, 0, rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which, nev,
+                      tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void ssaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+              a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+              a_int lworkl, a_int* info) {
+  aupd_entry<float, true>(false, 0, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                          workl, lworkl, info);
+}
+void sseupd_c(a_int rvec, char const* howmny, a_int const* select, float* d, float* z, a_int ldz, float sigma,
+              char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid, a_int ncv, float* v,
+              a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl, a_int lworkl, a_int* info) {
+  seupd_entry<float>(false, 0, rvec, howmny, select, d, z, ldz, sigma, bmat, n, which, nev, tol, resid, ncv, v,
+                     ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void snaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+              a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+              a_int lworkl, a_int* info) {
+  aupd_entry<float, false>(false, 0, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                           workl, lworkl, info);
+}
+void sneupd_c(a_int rvec, char const* howmny, a_int const* select, float* dr, float* di, float* z, a_int ldz,
+              float sigmar, float sigmai, float* workev, char const* bmat, a_int n, char const* which, a_int nev,
+              float tol, float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+              float* workl, a_int lworkl, a_int* info) {
+  neupd_entry<float>(false, 0, rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which, nev,
+                     tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+
+// ---- ICB/parpack.h (comm = handle from ab200_comm_create) --------------------------------------
+void pdsaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd,
+               double* workl, a_int lworkl, a_int* info) {
+  aupd_entry<double, true>(true, comm, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                           workl, lworkl, info);
+}
+void pdseupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, double* d, double* z, a_int ldz,
+               double sigma, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+               a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+               a_int lworkl, a_int* info) {
+  seupd_entry<double>(true, comm, rvec, howmny, select, d, z, ldz, sigma, bmat, n, which, nev, tol, resid, ncv, v,
+                      ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void pdnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd,
+               double* workl, a_int lworkl, a_int* info) {
+  aupd_entry<double, false>(true, comm, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                            workl, lworkl, info);
+}
+void pdneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, double* dr, double* di,
+               double* z, a_int ldz, double sigmar, double sigmai, double* workev, char const* bmat, a_int n,
+               char const* which, a_int nev, double tol, double* resid, a_int ncv, double* v, a_int ldv,
+               a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int lworkl, a_int* info) {
+  neupd_entry<double>(true, comm, rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which,
+                      nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void pssaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+               float* workl, a_int lworkl, a_int* info) {
+  aupd_entry<float, true>(true, comm, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                          workl, lworkl, info);
+}
+void psseupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, float* d, float* z, a_int ldz,
+               float sigma, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+               a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+               a_int lworkl, a_int* info) {
+  seupd_entry<float>(true, comm, rvec, howmny, select, d, z, ldz, sigma, bmat, n, which, nev, tol, resid, ncv, v,
+                     ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+void psnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+               float* workl, a_int lworkl, a_int* info) {
+  aupd_entry<float, false>(true, comm, ido, bmat, n, which, nev, &tol, resid, ncv, v, ldv, iparam, ipntr, workd,
+                           workl, lworkl, info);
+}
+void psneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, float* dr, float* di, float* z,
+               a_int ldz, float sigmar, float sigmai, float* workev, char const* bmat, a_int n, char const* which,
+               a_int nev, float tol, float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               float* workd, float* workl, a_int lworkl, a_int* info) {
+  neupd_entry<float>(true, comm, rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which,
+                     nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, lworkl, info);
+}
+
+// ---- legacy Fortran ABI (gfortran: everything by reference, CHARACTER lengths appended) ---------
+void dsaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid,
+             a_int* ncv, double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+             a_int* lworkl, a_int* info, size_t, size_t) {
+  aupd_entry<double, true>(false, 0, ido, bmat, *n, which, *nev, tol, resid, *ncv, v, *ldv, iparam, ipntr, workd,
+                           workl, *lworkl, info);
+}
+void dseupd_(a_int* rvec, const char* howmny, a_int* select, double* d, double* z, a_int* ldz, double* sigma,
+             const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid, a_int* ncv,
+             double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int* lworkl,
+             a_int* info, size_t, size_t, size_t) {
+  seupd_entry<double>(false, 0, *rvec, howmny, select, d, z, *ldz, *sigma, bmat, *n, which, *nev, *tol, resid,
+                      *ncv, v, *ldv, iparam, ipntr, workd, workl, *lworkl, info);
+}
+void dnaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid,
+             a_int* ncv, double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+             a_int* lworkl, a_int* info, size_t, size_t) {
+  aupd_entry<double, false>(false, 0, ido, bmat, *n, which, *nev, tol, resid, *ncv, v, *ldv, iparam, ipntr, workd,
+                            workl, *lworkl, info);
+}
+void dneupd_(a_int* rvec, const char* howmny, a_int* select, double* dr, double* di, double* z, a_int* ldz,
+             double* sigmar, double* sigmai, double* workev, const char* bmat, a_int* n, const char* which,
+             a_int* nev, double* tol, double* resid, a_int* ncv, double* v, a_int* ldv, a_int* iparam,
+             a_int* ipntr, double* workd, double* workl, a_int* lworkl, a_int* info, size_t, size_t, size_t) {
+  neupd_entry<double>(false, 0, *rvec, howmny, select, dr, di, z, *ldz, *sigmar, *sigmai, workev, bmat, *n, which,
+                      *nev, *tol, resid, *ncv, v, *ldv, iparam, ipntr, workd, workl, *lworkl, info);
+}
+
+// ---- ICB/debug_c.h, ICB/stat_c.h ---------------------------------------------------------------
+void debug_c(a_int logfil, a_int ndigit, a_int mgetv0, a_int msaupd, a_int msaup2, a_int msaitr, a_int mseigt,
+             a_int msapps, a_int msgets, a_int mseupd, a_int mnaupd, a_int mnaup2, a_int mnaitr, a_int mneigh,
+             a_int mnapps, a_int mngets, a_int mneupd, a_int mcaupd, a_int mcaup2, a_int mcaitr, a_int mceigh,
+             a_int mcapps, a_int mcgets, a_int mceupd) {
+  const int vals[24] = {logfil, ndigit, mgetv0, msaupd, msaup2, msaitr, mseigt, msapps, msgets, mseupd, mnaupd, mnaup2,
+                        mnaitr, mneigh, mnapps, mngets, mneupd, mcaupd, mcaup2, mcaitr, mceigh, mcapps, mcgets, mceupd};
+  std::memcpy(g_debug.v, vals, sizeof(vals));
+}
+void sstats_c(void) { g_last_counters = Counters(); }
+void sstatn_c(void) { g_last_counters = Counters(); }
+void stat_c(a_int* nopx, a_int* nbx, a_int* nrorth, a_int* nitref, a_int* nrstrt, float* tsaupd, float* tsaup2,
+            float* tsaitr, float* tseigt, float* tsgets, float* tsapps, float* tsconv, float* tnaupd, float* tnaup2,
+            float* tnaitr, float* tneigh, float* tngets, float* tnapps, float* tnconv, float* tcaupd, float* tcaup2,
+            float* tcaitr, float* tceigh, float* tcgets, float* tcapps, float* tcconv, float* tmvopx, float* tmvbx,
+            float* tgetv0, float* titref, float* trvec) {
+  *nopx = g_last_counters.nopx; *nbx = g_last_counters.nbx; *nrorth = g_last_counters.nrorth;
+  *nitref = g_last_counters.nitref; *nrstrt = g_last_counters.nrstrt;
+  // the reference's timers are dead in arpack-ng builds (UTIL/second_NONE.f:29-31): always 0
+  float* ts[] = {tsaupd, tsaup2, tsaitr, tseigt, tsgets, tsapps, tsconv, tnaupd, tnaup2, tnaitr, tneigh, tngets, tnapps,
+                 tnconv, tcaupd, tcaup2, tcaitr, tceigh, tcgets, tcapps, tcconv, tmvopx, tmvbx, tgetv0, titref, trvec};
+  for (float* t : ts)
+    if (t) *t = 0.0f;
+}
+
+// ---- extensions --------------------------------------------------------------------------------
+void ab200_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+void* ab200_get_stream(void) { return (void*)g_stream; }
+void ab200_set_kernel_mode(int mode) { g_kernel_mode = mode; }
+void ab200_release(const void* workl) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  table<double>().erase(workl);
+  table<float>().erase(workl);
+}
+void ab200_release_all(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  table<double>().clear();
+  table<float>().clear();
+}
+void ab200_launch_stats(unsigned long long* out4) {
+  const LaunchStats& s = launch_stats();
+  out4[0] = s.kernels; out4[1] = s.allreduces; out4[2] = s.fast_path; out4[3] = s.fallback;
+}
+void ab200_reset_seed(void) {
+  Globals<double>::seed = SeedState(); Globals<double>::seed_par = SeedState();
+  Globals<float>::seed = SeedState(); Globals<float>::seed_par = SeedState();
+  Globals<double>::smlnum_first = -1.0; Globals<float>::smlnum_first = -1.0f;
+}
+int ab200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+const char* ab200_version(void) { return "arpack_b200 0.1 (sm_100a)"; }
+}

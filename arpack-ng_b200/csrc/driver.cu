@@ -1,0 +1,323 @@
+// driver.cu -- the caller's side of the reverse-communication loop, on the device.
+//
+// In the reference the matrix belongs to the user: EXAMPLES/SIMPLE/dssimp.f:484-540 (av/tv),
+// EXAMPLES/NONSYM/dndrv1.f:453-470, PARPACK/EXAMPLES/MPI/pdsdrv1.f:418-483 (av with halo send/recv),
+// EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:806-841 (Eigen products).  These kernels are the B200
+// equivalents used by the arpackmm-style driver, the tests and bench.py: CSR SpMV (K3), synthetic
+// operator generators for BASELINE.json's configs, the hashed start vector, and the residual check.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/arpack_b200.h"
+#include "vecops_cuda.cuh"
+
+namespace ab200 {
+NcclComm* comm_from_handle(int handle);
+void nccl_halo_exchange(NcclComm* c, const void* send_lo, void* recv_lo, size_t n_lo, const void* send_hi,
+                        void* recv_hi, size_t n_hi, bool is_double, cudaStream_t s);
+
+namespace {
+
+inline cudaStream_t cur_stream() { return (cudaStream_t)ab200_get_stream(); }
+
+// ---------------------------------------------------------------------------------------------
+// CSR SpMV, LPR lanes per row (power of two <= 32).  Rows of the target operators are short
+// (5..16 nnz): a sub-warp per row keeps the val/col streams coalesced across neighbouring rows
+// while x is gathered through L1/L2.  Algorithmic traffic: nnz*(w+4) + (n+1)*4 + 2*n*w bytes.
+// xh: optional second source for columns >= nloc (halo buffer of the row-partitioned operator).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256) k_csr_spmv(int nrows, const int* __restrict__ rowptr,
+                                                  const int* __restrict__ col, const T* __restrict__ val,
+                                                  const T* __restrict__ x, T* __restrict__ y, int nloc,
+                                                  const T* __restrict__ xh) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long sub = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const long long nsub = ((long long)gridDim.x * blockDim.x) / LPR;
+  for (long long row = sub; row < nrows; row += nsub) {
+    const int p0 = rowptr[row], p1 = rowptr[row + 1];
+    T acc = T(0);
+    for (int p = p0 + lane; p < p1; p += LPR) {
+      const int c = col[p];
+      const T xv = (xh != nullptr && c >= nloc) ? xh[c - nloc] : x[c];
+      acc += val[p] * xv;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+    if (lane == 0) y[row] = acc;
+  }
+}
+
+template <typename T>
+int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, const T* x, T* y, int nloc,
+                const T* xh, long long nnz_hint) {
+  if (nrows <= 0) return 0;
+  const double avg = nnz_hint > 0 ? (double)nnz_hint / nrows : 8.0;
+  const int threads = 256;
+  cudaStream_t s = cur_stream();
+  auto grid_for = [&](int lpr) {
+    long long g = ((long long)nrows * lpr + threads - 1) / threads;
+    const long long cap = 148LL * 32;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+  };
+  if (avg <= 3.0) k_csr_spmv<T, 2><<<grid_for(2), threads, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+  else if (avg <= 6.0) k_csr_spmv<T, 4><<<grid_for(4), threads, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+  else if (avg <= 12.0) k_csr_spmv<T, 8><<<grid_for(8), threads, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+  else if (avg <= 24.0) k_csr_spmv<T, 16><<<grid_for(16), threads, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+  else k_csr_spmv<T, 32><<<grid_for(32), threads, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// nnz of a CSR matrix whose rowptr lives on the device, cached per rowptr address
+long long nnz_of(int nrows, const int* rowptr) {
+  static const int* last_ptr = nullptr;
+  static int last_rows = 0;
+  static long long last_nnz = 0;
+  if (rowptr == last_ptr && nrows == last_rows) return last_nnz;
+  int h = 0;
+  if (cudaMemcpyAsync(&h, rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, cur_stream()) != cudaSuccess) return 0;
+  cudaStreamSynchronize(cur_stream());
+  last_ptr = rowptr; last_rows = nrows; last_nnz = h;
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generators (row-major natural ordering, ascending column order inside a row)
+// ---------------------------------------------------------------------------------------------
+// 2-D 5-point Laplacian scaled by `scale` (dssimp.f:484-540 uses scale = (nx+1)^2; BASELINE config 2: 1)
+__global__ void k_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val) {
+  const long long n = (long long)nx * ny;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (long long)gridDim.x * blockDim.x) {
+    // entries before row r: 5 per row minus the missing neighbours
+    const long long iy = r / nx, ix = r % nx;  // row r = (iy, ix)
+    // rows 0..r-1: missing left = number of rows with ix==0, etc.
+    long long before = 5 * r;
+    before -= (iy + (ix > 0 ? 1 : 0));            // rows with ix == 0 among 0..r-1
+    before -= (iy);                               // rows with ix == nx-1 among 0..r-1 (complete grid lines only)
+    before -= (r < nx ? r : nx);                  // rows with iy == 0
+    before -= (iy == ny ? nx : 0) + ((iy == ny - 1) ? ix : 0);  // rows with iy == ny-1
+    if (r == n) {
+      rowptr[n] = (int)before;
+      return;
+    }
+    rowptr[r] = (int)before;
+    long long p = before;
+    if (iy > 0) { col[p] = (int)(r - nx); val[p] = -scale; ++p; }
+    if (ix > 0) { col[p] = (int)(r - 1); val[p] = -scale; ++p; }
+    col[p] = (int)r; val[p] = 4.0 * scale; ++p;
+    if (ix < nx - 1) { col[p] = (int)(r + 1); val[p] = -scale; ++p; }
+    if (iy < ny - 1) { col[p] = (int)(r + nx); val[p] = -scale; ++p; }
+  }
+}
+
+// 2-D convection-diffusion of dndrv1.f:453-470 / dnsimp.f:570 on the unit square, h = 1/(nx+1)
+__global__ void k_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double* val) {
+  const long long n = (long long)nx * nx;
+  const double h = 1.0 / (double)(nx + 1), h2 = h * h;
+  const double dd = 4.0 / h2, dl = -1.0 / h2 - 0.5 * rho / h, du = -1.0 / h2 + 0.5 * rho / h, ob = -1.0 / h2;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (long long)gridDim.x * blockDim.x) {
+    const long long iy = r / nx, ix = r % nx;
+    long long before = 5 * r;
+    before -= (iy + (ix > 0 ? 1 : 0));
+    before -= iy;
+    before -= (r < nx ? r : nx);
+    before -= (iy == nx ? nx : 0) + ((iy == nx - 1) ? ix : 0);
+    if (r == n) {
+      rowptr[n] = (int)before;
+      return;
+    }
+    rowptr[r] = (int)before;
+    long long p = before;
+    if (iy > 0) { col[p] = (int)(r - nx); val[p] = ob; ++p; }
+    if (ix > 0) { col[p] = (int)(r - 1); val[p] = dl; ++p; }
+    col[p] = (int)r; val[p] = dd; ++p;
+    if (ix < nx - 1) { col[p] = (int)(r + 1); val[p] = du; ++p; }
+    if (iy < nx - 1) { col[p] = (int)(r + nx); val[p] = ob; ++p; }
+  }
+}
+
+// 3-D 7-point Laplacian (6, -1) on nx x ny x nz, rows of the z-slab [z0, z0+nzloc).  Local column
+// numbering of the row-partitioned operator: own rows [0, nloc), then the lower halo plane
+// (z0-1) at [nloc, nloc+nx*ny) if z0 > 0, then the upper halo plane (z0+nzloc).
+__device__ inline long long lap3d_before(long long r, int nx, int ny, int nzloc, bool has_lo, bool has_hi) {
+  const long long plane = (long long)nx * ny;
+  const long long iz = r / plane, rem = r % plane, iy = rem / nx, ix = rem % nx;
+  long long before = 7 * r;
+  // missing x-neighbours: one per grid line end
+  const long long lines = iz * ny + iy;  // complete lines before r
+  before -= lines + (ix > 0 ? 1 : 0);    // ix == 0
+  before -= lines;                       // ix == nx-1
+  // missing y-neighbours: rows with iy == 0 / iy == ny-1
+  before -= iz * nx + (iy > 0 ? nx : ix);                       // iy == 0
+  before -= iz * nx + (iy == ny - 1 ? ix : 0);                  // iy == ny-1
+  // missing z-neighbours only at the global boundary (halo planes supply the others)
+  if (!has_lo) before -= (iz > 0 ? plane : rem);
+  if (!has_hi) before -= (iz == nzloc - 1 ? rem : 0) + (iz >= nzloc ? plane : 0);
+  return before;
+}
+__global__ void k_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val) {
+  const long long plane = (long long)nx * ny, nloc = plane * nzloc;
+  const bool has_lo = z0 > 0, has_hi = (z0 + nzloc) < nz;
+  const long long lo_base = nloc, hi_base = nloc + (has_lo ? plane : 0);
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= nloc; r += (long long)gridDim.x * blockDim.x) {
+    const long long before = lap3d_before(r, nx, ny, nzloc, has_lo, has_hi);
+    if (r == nloc) {
+      rowptr[nloc] = (int)before;
+      return;
+    }
+    rowptr[r] = (int)before;
+    const long long iz = r / plane, rem = r % plane, iy = rem / nx, ix = rem % nx;
+    long long p = before;
+    if (iz > 0) { col[p] = (int)(r - plane); val[p] = -1.0; ++p; }
+    else if (has_lo) { col[p] = (int)(lo_base + rem); val[p] = -1.0; ++p; }
+    if (iy > 0) { col[p] = (int)(r - nx); val[p] = -1.0; ++p; }
+    if (ix > 0) { col[p] = (int)(r - 1); val[p] = -1.0; ++p; }
+    col[p] = (int)r; val[p] = 6.0; ++p;
+    if (ix < nx - 1) { col[p] = (int)(r + 1); val[p] = -1.0; ++p; }
+    if (iy < ny - 1) { col[p] = (int)(r + nx); val[p] = -1.0; ++p; }
+    if (iz < nzloc - 1) { col[p] = (int)(r + plane); val[p] = -1.0; ++p; }
+    else if (has_hi) { col[p] = (int)(hi_base + rem); val[p] = -1.0; ++p; }
+  }
+}
+
+__device__ inline unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__global__ void k_fill_hash(long long n, long long i0, unsigned long long seed, double* x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long h = splitmix64(seed + (unsigned long long)(i0 + i));
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+    x[i] = 2.0 * u - 1.0;
+  }
+}
+
+// || A z - d z ||^2 per column, one block-wide deterministic reduction per column (small k)
+__global__ void __launch_bounds__(256) k_residual_sq(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                     const double* __restrict__ val, const double* __restrict__ z,
+                                                     double d, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) s += val[p] * z[col[p]];
+    s -= d * z[r];
+    acc += s * s;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+inline int gen_grid(long long n) {
+  long long g = (n + 255) / 256;
+  return (int)(g > 148LL * 16 ? 148LL * 16 : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" {
+
+int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
+  return launch_spmv<double>(nrows, rowptr, col, val, x, y, 0, nullptr, nnz_of(nrows, rowptr));
+}
+int ab200_csr_spmv_f32(int nrows, const int* rowptr, const int* col, const float* val, const float* x, float* y) {
+  return launch_spmv<float>(nrows, rowptr, col, val, x, y, 0, nullptr, nnz_of(nrows, rowptr));
+}
+
+int ab200_csr_spmv_hostvec_f64(int nrows, int ncols, const int* rowptr, const int* col, const double* val,
+                               const double* x_host, double* y_host) {
+  static double* xd = nullptr;
+  static double* yd = nullptr;
+  static size_t xcap = 0, ycap = 0;
+  cudaStream_t s = cur_stream();
+  if ((size_t)ncols > xcap) { cudaFree(xd); if (cudaMalloc(&xd, sizeof(double) * ncols) != cudaSuccess) return -1; xcap = ncols; }
+  if ((size_t)nrows > ycap) { cudaFree(yd); if (cudaMalloc(&yd, sizeof(double) * nrows) != cudaSuccess) return -1; ycap = nrows; }
+  if (cudaMemcpyAsync(xd, x_host, sizeof(double) * ncols, cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
+  if (launch_spmv<double>(nrows, rowptr, col, val, xd, yd, 0, nullptr, nnz_of(nrows, rowptr)) != 0) return -3;
+  if (cudaMemcpyAsync(y_host, yd, sizeof(double) * nrows, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -4;
+  return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -5;
+}
+
+int ab200_csr_spmv_halo_f64(int comm, int nloc, int halo_lo, int halo_hi, const int* rowptr, const int* col,
+                            const double* val, const double* x, double* y, double* halo_buf) {
+  try {
+    NcclComm* c = comm_from_handle(comm);
+    if (c && (halo_lo > 0 || halo_hi > 0)) {
+      // my first plane goes down, my last plane goes up; halo_buf = [plane from below | plane from above]
+      nccl_halo_exchange(c, x, halo_buf, (size_t)halo_lo, x + (nloc - halo_hi), halo_buf + halo_lo,
+                         (size_t)halo_hi, true, cur_stream());
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: halo exchange: %s\n", e.what());
+    return -1;
+  }
+  return launch_spmv<double>(nloc, rowptr, col, val, x, y, nloc, halo_buf, nnz_of(nloc, rowptr));
+}
+
+long long ab200_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val) {
+  const long long n = (long long)nx * ny, nnz = 5 * n - 2LL * nx - 2LL * ny;
+  if (nnz > 2147483647LL) return -2;
+  if (!rowptr) return nnz;
+  k_gen_laplace2d<<<gen_grid(n + 1), 256, 0, cur_stream()>>>(nx, ny, scale, rowptr, col, val);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? nnz : -1;
+}
+long long ab200_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double* val) {
+  const long long n = (long long)nx * nx, nnz = 5 * n - 4LL * nx;
+  if (nnz > 2147483647LL) return -2;
+  if (!rowptr) return nnz;
+  k_gen_convdiff2d<<<gen_grid(n + 1), 256, 0, cur_stream()>>>(nx, rho, rowptr, col, val);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? nnz : -1;
+}
+long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val) {
+  const long long plane = (long long)nx * ny, nloc = plane * nzloc;
+  const bool has_lo = z0 > 0, has_hi = (z0 + nzloc) < nz;
+  long long nnz = 7 * nloc - 2LL * ny * nzloc - 2LL * nx * nzloc;
+  if (!has_lo) nnz -= plane;
+  if (!has_hi) nnz -= plane;
+  if (nnz > 2147483647LL) return -2;
+  if (!rowptr) return nnz;
+  k_gen_laplace3d<<<gen_grid(nloc + 1), 256, 0, cur_stream()>>>(nx, ny, nz, z0, nzloc, rowptr, col, val);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? nnz : -1;
+}
+int ab200_fill_hash_f64(long long n, long long i0, unsigned long long seed, double* x) {
+  k_fill_hash<<<gen_grid(n), 256, 0, cur_stream()>>>(n, i0, seed, x);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+int ab200_residuals_f64(int n, const int* rowptr, const int* col, const double* val, int k, const double* z,
+                        long long ldz, const double* d_host, double* out_host) {
+  const int grid = gen_grid(n);
+  double* partial = nullptr;
+  if (cudaMalloc(&partial, sizeof(double) * grid) != cudaSuccess) return -1;
+  std::vector<double> h((size_t)grid);
+  cudaStream_t s = cur_stream();
+  for (int c = 0; c < k; ++c) {
+    k_residual_sq<<<grid, 256, 0, s>>>(n, rowptr, col, val, z + (size_t)c * ldz, d_host[c], partial);
+    launch_stats().kernels++;
+    cudaMemcpyAsync(h.data(), partial, sizeof(double) * grid, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    double acc = 0.0;
+    for (int b = 0; b < grid; ++b) acc += h[b];
+    out_host[c] = sqrt(acc);
+  }
+  cudaFree(partial);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+}

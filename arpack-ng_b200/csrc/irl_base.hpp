@@ -1,0 +1,361 @@
+// irl_base.hpp -- shared host control of the implicitly restarted Lanczos/Arnoldi iteration.
+//
+// What the reference spreads over SAVE'd flags and computed GOTOs is written
+// here as resumable routines: each reverse-communication hand-off is a CO_YIELD, all state lives in
+// the solver object, and every n-length operation goes through VecOps (device kernels).
+//
+//   start_vector()  <->  SRC/dgetv0.f:119-421, PARPACK/SRC/MPI/pdgetv0.f:131-463
+//   extend()        <->  SRC/dsaitr.f:204-853 and SRC/dnaitr.f:209-840 (+ pdsaitr.f / pdnaitr.f)
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "hostmath.hpp"
+#include "vecops.hpp"
+
+namespace ab200 {
+
+// resumable-routine plumbing (switch-based; no locals may live across a yield)
+#define CO_BEGIN(pc) \
+  switch (pc) {      \
+    case 0:
+#define CO_YIELD(pc)  \
+  do {                \
+    pc = __LINE__;    \
+    return false;     \
+    case __LINE__:;   \
+  } while (0)
+// run a nested resumable routine to completion, yielding whenever it yields
+#define CO_CALL(pc, expr)      \
+  do {                         \
+    pc = __LINE__;             \
+    case __LINE__:             \
+      if (!(expr)) return false; \
+  } while (0)
+#define CO_END(pc) \
+  }                \
+  pc = 0;          \
+  return true;
+// leave a resumable routine for good from the middle of its body
+#define CO_END_EARLY(pc) \
+  do {                   \
+    pc = 0;              \
+    return true;         \
+  } while (0)
+
+// COMMON /timing/ counters of the reference (stat.h:11)
+struct Counters {
+  int nopx = 0, nbx = 0, nrorth = 0, nitref = 0, nrstrt = 0;
+};
+
+// LAPACK xLARNV seed, SAVE'd across solves in the reference (dgetv0.f:164,202-208); one per precision
+struct SeedState {
+  bool inited = false;
+  int iseed[4] = {0, 0, 0, 0};
+};
+
+template <typename T>
+class IrlBase {
+ public:
+  IrlBase(VecOps<T>* ops, bool parpack) : ops_(ops), par_(parpack) {}
+  virtual ~IrlBase() {}
+
+  Counters cnt;
+  const Counters& counters() const { return cnt; }
+
+  // *eupd on a context that never ran *aupd (fresh process): make sure the mailbox exists
+  void ensure_mailbox(int ncv) {
+    if (!mb_) {
+      ncv_ = ncv;
+      setup_mailbox();
+    }
+  }
+
+ protected:
+  VecOps<T>* ops_;
+  const bool par_;  // PARPACK semantics (pd*.f): per-rank seeds, no initial OP*x for bmat='I', ...
+
+  // problem description (fixed at ido = 0)
+  int n_ = 0, ncv_ = 0;
+  char bmat_ = 'I';
+  int mode_ = 1;
+  // device views of the caller's arrays
+  T* resid_ = nullptr;
+  T* v_ = nullptr;
+  int64_t ldv_ = 0;
+  T* workd_ = nullptr;
+  // reverse communication outputs
+  int ido_ = 0;
+  int ipntr_[3] = {0, 0, 0};
+
+  // mailbox layout: three segments of seg_ entries each
+  T* mb_ = nullptr;
+  int seg_ = 0;
+  std::vector<T> mbh_;  // host copy
+  T* mbA() { return mb_; }
+  T* mbB() { return mb_ + seg_; }
+  T* mbC() { return mb_ + 2 * seg_; }
+  T* hA() { return mbh_.data(); }
+  T* hB() { return mbh_.data() + seg_; }
+  T* hC() { return mbh_.data() + 2 * seg_; }
+
+  SeedState* seed_ = nullptr;
+
+  T* vcol(int j1) { return v_ + (int64_t)(j1 - 1) * ldv_; }  // 1-based column
+  T* slot(int off1) { return workd_ + (off1 - 1); }           // 1-based workd offset
+
+  void setup_mailbox() {
+    seg_ = ncv_ + 2;
+    mb_ = ops_->mailbox((size_t)3 * seg_);
+    mbh_.assign((size_t)3 * seg_, T(0));
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // start / restart vector
+  // ---------------------------------------------------------------------------------------------
+  int gv_pc_ = 0, gv_itry_ = 1, gv_j_ = 1, gv_iter_ = 0, gv_ierr_ = 0;
+  bool gv_initv_ = false;
+  T gv_rnorm0_ = 0, rnorm_ = 0;
+
+  T fetch_norm_from_dot(T* mbslot) {
+    ops_->allreduce_sum(mbslot, 1);
+    ops_->fetch(hC(), mbslot, 1);
+    return std::sqrt(std::fabs(hC()[0]));
+  }
+
+  // returns true when finished (ierr in gv_ierr_, norm in rnorm_); false on a hand-off
+  bool start_vector() {
+    CO_BEGIN(gv_pc_)
+    if (!seed_->inited) {
+      if (!par_) {  // dgetv0.f:202-208
+        seed_->iseed[0] = 1; seed_->iseed[1] = 3; seed_->iseed[2] = 5; seed_->iseed[3] = 7;
+      } else {  // pdgetv0.f:233-245, digits of 1000 + 2*rank + 1
+        int igen = 1000 + 2 * ops_->rank() + 1;
+        seed_->iseed[0] = igen / 1000; igen %= 1000;
+        seed_->iseed[1] = igen / 100;  igen %= 100;
+        seed_->iseed[2] = igen / 10;
+        seed_->iseed[3] = igen % 10;
+      }
+      seed_->inited = true;
+    }
+    gv_ierr_ = 0;
+    gv_iter_ = 0;
+    if (!gv_initv_) ops_->larnv_uniform_m1_1(n_, seed_->iseed, resid_);
+    // force the vector into range(OP) (dgetv0.f:245-251; PARPACK only for bmat='G', pdgetv0.f:285)
+    if ((!par_ && gv_itry_ == 1) || (par_ && bmat_ == 'G')) {
+      cnt.nopx++;
+      ops_->copy(n_, resid_, slot(1));
+      ipntr_[0] = 1; ipntr_[1] = n_ + 1;
+      ido_ = -1;
+      CO_YIELD(gv_pc_);
+      ops_->copy(n_, slot(n_ + 1), resid_);
+    } else if (!par_ && gv_itry_ > 1 && bmat_ == 'G') {
+      ops_->copy(n_, resid_, slot(n_ + 1));
+    }
+    if (bmat_ == 'G') {
+      cnt.nbx++;
+      ipntr_[0] = n_ + 1; ipntr_[1] = 1;
+      ido_ = 2;
+      CO_YIELD(gv_pc_);
+      ops_->dot(n_, resid_, slot(1), mbC());
+    } else {
+      ops_->dot(n_, resid_, resid_, mbC());
+    }
+    gv_rnorm0_ = fetch_norm_from_dot(mbC());
+    rnorm_ = gv_rnorm0_;
+    if (gv_j_ > 1) {
+      // orthogonalise against V(:,1:j-1) with iterative refinement (dgetv0.f:326-397)
+      for (;;) {
+        ops_->dots(n_, gv_j_ - 1, v_, ldv_, bmat_ == 'G' ? slot(1) : resid_, resid_, mbA());
+        ops_->allreduce_sum(mbA(), (size_t)gv_j_ - 1);
+        if (bmat_ == 'G') {
+          ops_->update(n_, gv_j_ - 1, v_, ldv_, mbA(), resid_, resid_, nullptr);
+          cnt.nbx++;
+          ops_->copy(n_, resid_, slot(n_ + 1));
+          ipntr_[0] = n_ + 1; ipntr_[1] = 1;
+          ido_ = 2;
+          CO_YIELD(gv_pc_);
+          ops_->dot(n_, resid_, slot(1), mbC());
+        } else {
+          ops_->update(n_, gv_j_ - 1, v_, ldv_, mbA(), resid_, resid_, mbC());
+        }
+        rnorm_ = fetch_norm_from_dot(mbC());
+        if (rnorm_ > dgks_threshold<T>() * gv_rnorm0_) break;
+        gv_iter_++;
+        if (gv_iter_ <= (par_ ? 1 : 5)) {  // dgetv0.f:378 / pdgetv0.f
+          gv_rnorm0_ = rnorm_;
+        } else {
+          ops_->zero(n_, resid_);
+          rnorm_ = 0;
+          gv_ierr_ = -1;
+          break;
+        }
+      }
+    }
+    CO_END(gv_pc_)
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // k -> k+np step extension of the factorisation
+  // ---------------------------------------------------------------------------------------------
+  // hooks: where the projected matrix lives differs between the symmetric (tridiagonal, 2 columns)
+  // and the nonsymmetric (full Hessenberg) solver.
+  virtual void h_store(int j, const T* hcol, T beta, bool after_restart) = 0;  // CGS column of step j
+  virtual void h_add(int j, const T* scol, bool after_restart) = 0;            // DGKS correction
+  virtual void sweep_done(int k, int np) = 0;
+  virtual T tiny_norm() = 0;  // dsaitr: safmin; dnaitr: unfl after dlabad
+
+  int ai_pc_ = 0, ai_k_ = 0, ai_np_ = 0, ai_j_ = 0, ai_itry_ = 0, ai_iter_ = 0, ai_info_ = 0;
+  bool ai_rstart_ = false;
+  T ai_wnorm_ = 0, ai_beta_ = 0, ai_rnorm1_ = 0;
+
+  static constexpr int IPJ = 1;
+  int irj() const { return 1 + n_; }
+  int ivj() const { return 1 + 2 * n_; }
+
+  // generic B-norm of resid: bmat='G' needs a hand-off, so only the tail is here
+  // returns true when finished; ai_info_ > 0 <=> no restart vector could be found (info = j-1)
+  bool extend() {
+    CO_BEGIN(ai_pc_)
+    ai_info_ = 0;
+    for (ai_j_ = ai_k_ + 1; ai_j_ <= ai_k_ + ai_np_; ++ai_j_) {
+      ai_beta_ = rnorm_;
+      ai_rstart_ = false;
+      if (!(rnorm_ > T(0))) {
+        // invariant subspace: find a new vector orthogonal to the current basis (dsaitr.f:378-427)
+        ai_beta_ = 0;
+        cnt.nrstrt++;
+        ai_rstart_ = true;
+        for (ai_itry_ = 1; ai_itry_ <= 3; ++ai_itry_) {
+          gv_itry_ = ai_itry_; gv_initv_ = false; gv_j_ = ai_j_;
+          CO_CALL(ai_pc_, start_vector());
+          if (gv_ierr_ >= 0) break;
+        }
+        if (gv_ierr_ < 0) {
+          ai_info_ = ai_j_ - 1;
+          ai_pc_ = 0;
+          return true;
+        }
+      }
+      // v_j = r/||r||, p_j = B r/||r||, x = v_j   (dsaitr.f:438-468)
+      {
+        const T tiny = tiny_norm();
+        if (rnorm_ >= tiny) {
+          ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(ai_j_), slot(ivj()), slot(IPJ), bmat_ == 'I');
+        } else {
+          // dlascl fallback of the reference (dsaitr.f:450-453): scale in two safe steps
+          const T big = std::ldexp(T(1), sizeof(T) == 8 ? 500 : 60);
+          ops_->start_step(n_, T(1) / (rnorm_ * big), resid_, vcol(ai_j_), slot(ivj()), slot(IPJ),
+                           bmat_ == 'I');
+          ops_->scal(n_, big, vcol(ai_j_));
+          ops_->scal(n_, big, slot(ivj()));
+          ops_->scal(n_, big, slot(IPJ));
+        }
+      }
+      cnt.nopx++;
+      ipntr_[0] = ivj(); ipntr_[1] = irj(); ipntr_[2] = IPJ;
+      ido_ = 1;
+      CO_YIELD(ai_pc_);
+      // workd(irj) = OP*v_j
+      if (bmat_ == 'I' && mode_ != 2) {
+        // ---- fused path: CGS + speculative DGKS, one host round trip (K4..K10) ----
+        ops_->orth_step(n_, ai_j_, v_, ldv_, slot(irj()), resid_, mbA(), mbB(), mbC());
+        ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 2);
+        ai_wnorm_ = std::sqrt(hA()[ai_j_]);
+        h_store(ai_j_, hA(), ai_beta_, ai_rstart_);
+        rnorm_ = std::sqrt(hB()[ai_j_]);
+        if (!(rnorm_ > dgks_threshold<T>() * ai_wnorm_)) {
+          cnt.nrorth++;
+          h_add(ai_j_, hB(), ai_rstart_);
+          ai_rnorm1_ = std::sqrt(hC()[0]);
+          if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
+            rnorm_ = ai_rnorm1_;
+          } else {
+            // one more refinement pass (iter = 1), then give up (dsaitr.f:768-780)
+            cnt.nitref++;
+            rnorm_ = ai_rnorm1_;
+            ops_->dots(n_, ai_j_, v_, ldv_, resid_, resid_, mbA());
+            ops_->allreduce_sum(mbA(), (size_t)ai_j_);
+            ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, mbC());
+            ops_->allreduce_sum(mbC(), 1);
+            ops_->fetch(hA(), mbA(), (size_t)ai_j_);
+            ops_->fetch(hC(), mbC(), 1);
+            h_add(ai_j_, hA(), ai_rstart_);
+            ai_rnorm1_ = std::sqrt(std::fabs(hC()[0]));
+            if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
+              rnorm_ = ai_rnorm1_;
+            } else {
+              cnt.nitref++;
+              ops_->zero(n_, resid_);
+              rnorm_ = 0;
+            }
+          }
+        }
+      } else {
+        // ---- generic path (bmat='G' and/or mode 2): B-inner products need hand-offs ----
+        ops_->copy(n_, slot(irj()), resid_);
+        if (mode_ != 2) {
+          // bmat == 'G' here
+          cnt.nbx++;
+          ipntr_[0] = irj(); ipntr_[1] = IPJ;
+          ido_ = 2;
+          CO_YIELD(ai_pc_);
+        }
+        // wnorm and the CGS coefficients use B*OP*v_j: workd(ipj), or workd(ivj) = A*v_j in mode 2
+        ops_->dots(n_, ai_j_, v_, ldv_, mode_ == 2 ? slot(ivj()) : slot(IPJ), resid_, mbA());
+        ops_->allreduce_sum(mbA(), (size_t)ai_j_ + 1);
+        ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, bmat_ == 'I' ? mbC() : nullptr);
+        ops_->fetch(hA(), mbA(), (size_t)ai_j_ + 1);
+        ai_wnorm_ = std::sqrt(std::fabs(hA()[ai_j_]));
+        h_store(ai_j_, hA(), ai_beta_, ai_rstart_);
+        ai_iter_ = 0;
+        if (bmat_ == 'G') {
+          cnt.nbx++;
+          ops_->copy(n_, resid_, slot(irj()));
+          ipntr_[0] = irj(); ipntr_[1] = IPJ;
+          ido_ = 2;
+          CO_YIELD(ai_pc_);
+          ops_->dot(n_, resid_, slot(IPJ), mbC());
+        }
+        rnorm_ = fetch_norm_from_dot(mbC());
+        if (!(rnorm_ > dgks_threshold<T>() * ai_wnorm_)) {
+          cnt.nrorth++;
+          for (;;) {
+            ops_->dots(n_, ai_j_, v_, ldv_, bmat_ == 'G' ? slot(IPJ) : resid_, resid_, mbA());
+            ops_->allreduce_sum(mbA(), (size_t)ai_j_);
+            ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, bmat_ == 'I' ? mbC() : nullptr);
+            ops_->fetch(hA(), mbA(), (size_t)ai_j_);
+            h_add(ai_j_, hA(), ai_rstart_);
+            if (bmat_ == 'G') {
+              cnt.nbx++;
+              ops_->copy(n_, resid_, slot(irj()));
+              ipntr_[0] = irj(); ipntr_[1] = IPJ;
+              ido_ = 2;
+              CO_YIELD(ai_pc_);
+              ops_->dot(n_, resid_, slot(IPJ), mbC());
+            }
+            ai_rnorm1_ = fetch_norm_from_dot(mbC());
+            if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
+              rnorm_ = ai_rnorm1_;
+              break;
+            }
+            cnt.nitref++;
+            rnorm_ = ai_rnorm1_;
+            ai_iter_++;
+            if (ai_iter_ > 1) {
+              ops_->zero(n_, resid_);
+              rnorm_ = 0;
+              break;
+            }
+          }
+        }
+      }
+    }
+    sweep_done(ai_k_, ai_np_);
+    CO_END(ai_pc_)
+  }
+};
+
+}  // namespace ab200

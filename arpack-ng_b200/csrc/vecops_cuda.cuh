@@ -1,0 +1,127 @@
+// vecops_cuda.cuh -- CUDA (sm_100a) implementation of the VecOps device boundary.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vecops.hpp"
+
+namespace ab200 {
+
+struct CudaError : std::runtime_error {
+  explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+#define AB200_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw ::ab200::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + \
+                               __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+  } while (0)
+
+// NCCL communicator wrapper (comm_nccl.cpp); opaque here
+struct NcclComm;
+void nccl_allreduce_sum(NcclComm* c, void* buf, size_t count, bool is_double, cudaStream_t s);
+int nccl_rank(const NcclComm* c);
+int nccl_nranks(const NcclComm* c);
+
+// process-wide launch statistics (bench.py reports gpu_launches from here)
+struct LaunchStats {
+  unsigned long long kernels = 0;
+  unsigned long long allreduces = 0;
+  unsigned long long fast_path = 0;   // launches of the TMA-tiled kernels
+  unsigned long long fallback = 0;    // launches of the generic kernels on the tall-skinny ops
+};
+LaunchStats& launch_stats();
+
+template <typename T>
+class CudaVecOps final : public VecOps<T> {
+ public:
+  explicit CudaVecOps(cudaStream_t stream, NcclComm* comm);
+  ~CudaVecOps() override;
+
+  T* alloc(size_t count) override;
+  void release(T* p) override;
+  void upload(T* dst_dev, const T* src_host, size_t count) override;
+  void download(T* dst_host, const T* src_dev, size_t count) override;
+  void upload2d(T* dst_dev, size_t ld_dst, const T* src_host, size_t ld_src, size_t rows, size_t cols) override;
+  void download2d(T* dst_host, size_t ld_dst, const T* src_dev, size_t ld_src, size_t rows, size_t cols) override;
+  void sync() override;
+  bool is_device_pointer(const void* p) override;
+
+  T* mailbox(size_t count) override;
+  void fetch(T* host_dst, const T* mb, size_t count) override;
+  void post(T* mb, const T* host_src, size_t count) override;
+  void allreduce_sum(T* mb, size_t count) override;
+  int rank() const override;
+  int nranks() const override;
+
+  void copy(int64_t n, const T* x, T* y) override;
+  void zero(int64_t n, T* x) override;
+  void scal(int64_t n, T alpha, T* x) override;
+  void axpby_norm(int64_t n, T a, T b, const T* x, T* y, T* mb_nrm2_out) override;
+  void dot(int64_t n, const T* x, const T* y, T* mb_out) override;
+  void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
+  void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx, bool bx_from_resid) override;
+  void ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) override;
+
+  void dots(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out) override;
+  void update(int64_t n, int j, const T* v, int64_t ldv, const T* mb_coef, const T* src, T* dst,
+              T* mb_nrm2) override;
+  void orth_step(int64_t n, int j, const T* v, int64_t ldv, const T* w, T* resid, T* mbA, T* mbB,
+                 T* mbC) override;
+  void vq_update(int64_t n, int kin, int kout, T* v, int64_t ldv, const T* q_host, int ldq, bool with_resid,
+                 T sigma, T beta, int beta_col, T* resid, T* mb_nrm2) override;
+  void vq_out(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* m_host, int ldm, T* out,
+              int64_t ldo) override;
+  void copy2d(int64_t n, int cols, const T* src, int64_t lds, T* dst, int64_t ldd) override;
+
+  cudaStream_t stream() const { return stream_; }
+  void set_stream(cudaStream_t s) { stream_ = s; }
+  // 0 = auto (TMA-tiled kernels when the layout allows), 1 = force the generic kernels
+  void set_kernel_mode(int m) { kernel_mode_ = m; }
+
+ private:
+  cudaStream_t stream_;
+  NcclComm* comm_;
+  int kernel_mode_ = 0;
+  int num_sms_ = 148;
+  // mailbox
+  T* mb_dev_ = nullptr;
+  size_t mb_count_ = 0;
+  T* mb_pinned_ = nullptr;
+  // two-stage reduction scratch: partial_[grid][pcols_] and a ticket counter
+  T* partial_ = nullptr;
+  size_t partial_count_ = 0;
+  unsigned int* ticket_ = nullptr;
+  // small device buffer for Q / coefficient matrices
+  T* qbuf_ = nullptr;
+  size_t qbuf_count_ = 0;
+  T* qpinned_ = nullptr;
+  size_t qpinned_count_ = 0;
+  // cached TMA descriptors for the fast path (opaque storage, see vecops_tma.cu)
+  struct TmaCache;
+  TmaCache* tma_ = nullptr;
+
+  void ensure_partial(size_t count);
+  T* stage_matrix(const T* host, int rows, int cols, int ld);  // -> device, packed rows x cols, column-major
+  bool fast_path_ok(int64_t n, int j, const T* v, int64_t ldv) const;
+  int reduce_grid(int64_t n) const;
+
+  // generic kernels (vecops_cuda.cu)
+  void dots_generic(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out);
+  void update_generic(int64_t n, int j, const T* v, int64_t ldv, const T* coef, const T* src, T* dst, T* nrm2,
+                      const T* pred_w2, const T* pred_r2, T* flag_out);
+  // TMA-tiled kernels (vecops_tma.cu)
+  bool orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, const T* w, T* resid, T* mbA, T* mbB, T* mbC);
+  bool dots_tma(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out);
+  bool vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* qdev, T* out, int64_t ldo,
+              bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2);
+  void tma_release();
+};
+
+}  // namespace ab200

@@ -1,0 +1,172 @@
+/*
+ * arpack_b200.h -- C ABI of libarpack_b200.so, the B200-native drop-in for ARPACK-NG's implicitly
+ * restarted Lanczos/Arnoldi hot path (dsaupd/dseupd, dnaupd/dneupd, PARPACK pdsaupd/pdnaupd).
+ *
+ * Every entry point below is what a binding of the reference for this path binds; the reference
+ * interface each one replaces is cited as file:line relative to the arpack-ng source tree.
+ * Plain pointers and sizes only; no CUDA or torch types appear in any signature.
+ *
+ * Array arguments resid, v, workd (and z) may be HOST pointers (an unmodified CPU caller: the
+ * library mirrors them in HBM and copies the hand-off vectors across PCIe) or DEVICE pointers
+ * (used in place; on ido = -1/1/2 the operand workd + ipntr[0] - 1 and the result slot
+ * workd + ipntr[1] - 1 are device addresses, ordered on the stream of ab200_get_stream()).
+ * workl, iparam, ipntr, select, d/dr/di, workev are always host memory.
+ *
+ * Error behaviour follows the reference (info < 0 with ido = 99 for argument errors, info = 1 max
+ * iterations, 3 no shifts, -8/-9/-9999 as in SRC/dsaupd.f:243-276), plus info = -9990 when no CUDA
+ * device is usable or a CUDA call failed (message on stderr).  There is no CPU fallback.
+ */
+#ifndef ARPACK_B200_H
+#define ARPACK_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int a_int;  /* arpackdef.h.in:8-14 (LP64 build) */
+typedef int a_fint; /* MPI_Fint of ICB/parpack.h:7-8; here: handle from ab200_comm_create() */
+
+/* ---- ICB/arpack.h:14-21 (bind(c) shims SRC/icbads.F90:3-92, icbadn.F90:3-97, icbass.F90, icbasn.F90) ---- */
+void dsaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+              a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+              a_int lworkl, a_int* info);
+void dseupd_c(a_int rvec, char const* howmny, a_int const* select, double* d, double* z, a_int ldz, double sigma,
+              char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid, a_int ncv,
+              double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int lworkl,
+              a_int* info);
+void dnaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+              a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+              a_int lworkl, a_int* info);
+void dneupd_c(a_int rvec, char const* howmny, a_int const* select, double* dr, double* di, double* z, a_int ldz,
+              double sigmar, double sigmai, double* workev, char const* bmat, a_int n, char const* which,
+              a_int nev, double tol, double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr,
+              double* workd, double* workl, a_int lworkl, a_int* info);
+void ssaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+              a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+              a_int lworkl, a_int* info);
+void sseupd_c(a_int rvec, char const* howmny, a_int const* select, float* d, float* z, a_int ldz, float sigma,
+              char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid, a_int ncv, float* v,
+              a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl, a_int lworkl, a_int* info);
+void snaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+              a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+              a_int lworkl, a_int* info);
+void sneupd_c(a_int rvec, char const* howmny, a_int const* select, float* dr, float* di, float* z, a_int ldz,
+              float sigmar, float sigmai, float* workev, char const* bmat, a_int n, char const* which, a_int nev,
+              float tol, float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+              float* workl, a_int lworkl, a_int* info);
+
+/* ---- ICB/parpack.h:12-27 (PARPACK/SRC/MPI/icbpds.F90, icbpdn.F90, icbpss.F90, icbpsn.F90).
+ * n is the LOCAL row count; all ranks call in lock-step.  MPI_ALLREDUCE of the reference
+ * (pdsaitr.f:604,720; pdnorm2.f:72-80; pdgetv0.f:369) is an NCCL all-reduce on the solve's stream. */
+void pdsaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd,
+               double* workl, a_int lworkl, a_int* info);
+void pdseupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, double* d, double* z, a_int ldz,
+               double sigma, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
+               a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+               a_int lworkl, a_int* info);
+void pdnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               double* resid, a_int ncv, double* v, a_int ldv, a_int* iparam, a_int* ipntr, double* workd,
+               double* workl, a_int lworkl, a_int* info);
+void pdneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, double* dr, double* di,
+               double* z, a_int ldz, double sigmar, double sigmai, double* workev, char const* bmat, a_int n,
+               char const* which, a_int nev, double tol, double* resid, a_int ncv, double* v, a_int ldv,
+               a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int lworkl, a_int* info);
+void pssaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+               float* workl, a_int lworkl, a_int* info);
+void psseupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, float* d, float* z, a_int ldz,
+               float sigma, char const* bmat, a_int n, char const* which, a_int nev, float tol, float* resid,
+               a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd, float* workl,
+               a_int lworkl, a_int* info);
+void psnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
+               float* workl, a_int lworkl, a_int* info);
+void psneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, float* dr, float* di, float* z,
+               a_int ldz, float sigmar, float sigmai, float* workev, char const* bmat, a_int n, char const* which,
+               a_int nev, float tol, float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               float* workd, float* workl, a_int lworkl, a_int* info);
+
+/* ---- legacy Fortran ABI (VISUAL_STUDIO/arpack-ng_exports.def; SRC/dsaupd.f:408, dseupd.f:218,
+ * dnaupd.f:406, dneupd.f:302): all arguments by reference, CHARACTER lengths appended by value ---- */
+void dsaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid,
+             a_int* ncv, double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+             a_int* lworkl, a_int* info, size_t bmat_len, size_t which_len);
+void dseupd_(a_int* rvec, const char* howmny, a_int* select, double* d, double* z, a_int* ldz, double* sigma,
+             const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid, a_int* ncv,
+             double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl, a_int* lworkl,
+             a_int* info, size_t howmny_len, size_t bmat_len, size_t which_len);
+void dnaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, double* resid,
+             a_int* ncv, double* v, a_int* ldv, a_int* iparam, a_int* ipntr, double* workd, double* workl,
+             a_int* lworkl, a_int* info, size_t bmat_len, size_t which_len);
+void dneupd_(a_int* rvec, const char* howmny, a_int* select, double* dr, double* di, double* z, a_int* ldz,
+             double* sigmar, double* sigmai, double* workev, const char* bmat, a_int* n, const char* which,
+             a_int* nev, double* tol, double* resid, a_int* ncv, double* v, a_int* ldv, a_int* iparam,
+             a_int* ipntr, double* workd, double* workl, a_int* lworkl, a_int* info, size_t howmny_len,
+             size_t bmat_len, size_t which_len);
+
+/* ---- ICB/debug_c.h:7 (ICB/debug_icb.F90), ICB/stat_c.h:7-14 (ICB/stat_icb.F90) ---- */
+void debug_c(a_int logfil, a_int ndigit, a_int mgetv0, a_int msaupd, a_int msaup2, a_int msaitr, a_int mseigt,
+             a_int msapps, a_int msgets, a_int mseupd, a_int mnaupd, a_int mnaup2, a_int mnaitr, a_int mneigh,
+             a_int mnapps, a_int mngets, a_int mneupd, a_int mcaupd, a_int mcaup2, a_int mcaitr, a_int mceigh,
+             a_int mcapps, a_int mcgets, a_int mceupd);
+void sstats_c(void);
+void sstatn_c(void);
+void stat_c(a_int* nopx, a_int* nbx, a_int* nrorth, a_int* nitref, a_int* nrstrt, float* tsaupd, float* tsaup2,
+            float* tsaitr, float* tseigt, float* tsgets, float* tsapps, float* tsconv, float* tnaupd, float* tnaup2,
+            float* tnaitr, float* tneigh, float* tngets, float* tnapps, float* tnconv, float* tcaupd, float* tcaup2,
+            float* tcaitr, float* tceigh, float* tcgets, float* tcapps, float* tcconv, float* tmvopx, float* tmvbx,
+            float* tgetv0, float* titref, float* trvec);
+
+/* ---- extensions (no counterpart in the reference) ---- */
+/* CUDA stream (cudaStream_t as void*) on which the library enqueues and on which the hand-off is ordered */
+void ab200_set_stream(void* cuda_stream);
+void* ab200_get_stream(void);
+/* 0 = automatic (TMA-tiled kernels when the layout allows), 1 = generic kernels only */
+void ab200_set_kernel_mode(int mode);
+/* free the device mirrors / solver state keyed to this workl (also done when workl is reused with ido = 0) */
+void ab200_release(const void* workl);
+void ab200_release_all(void);
+/* out4 = {kernels launched, all-reduces issued, TMA-path launches, generic-path launches} since load */
+void ab200_launch_stats(unsigned long long* out4);
+/* forget the SAVE'd dgetv0 seed / dnaitr smlnum, as if the process had just started */
+void ab200_reset_seed(void);
+int ab200_device_count(void);
+const char* ab200_version(void);
+
+/* NCCL communicators standing in for PARPACK's MPI communicator */
+int ab200_nccl_unique_id(void* out128);                        /* rank 0: 128-byte id to broadcast */
+int ab200_comm_create(const void* id128, int rank, int nranks); /* collective; returns the comm handle (>= 1) */
+void ab200_comm_destroy(int handle);
+int ab200_comm_rank(int handle);
+int ab200_comm_size(int handle);
+
+/* ---- driver layer: the user's OP for the arpackmm-style tool (EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:806-841
+ * does these products with Eigen on the CPU).  All pointers are DEVICE pointers unless named *_host. ---- */
+/* y = A x, CSR with int32 indices (K3 of SURVEY.md §2.3) */
+int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y);
+int ab200_csr_spmv_f32(int nrows, const int* rowptr, const int* col, const float* val, const float* x, float* y);
+/* as above with host vectors: H2D(x), SpMV, D2H(y) -- the OP of an unmodified host RCI loop */
+int ab200_csr_spmv_hostvec_f64(int nrows, int ncols, const int* rowptr, const int* col, const double* val,
+                               const double* x_host, double* y_host);
+/* row-partitioned SpMV with neighbour halos (PARPACK/EXAMPLES/MPI/pdsdrv1.f:463-483): columns >= nloc address
+ * the halo buffer [lower | upper]; the planes are exchanged with ncclSend/ncclRecv on the solve's stream */
+int ab200_csr_spmv_halo_f64(int comm, int nloc, int halo_lo, int halo_hi, const int* rowptr, const int* col,
+                            const double* val, const double* x, double* y, double* halo_buf);
+/* synthetic operators of BASELINE.json's configs, generated on the device; each returns nnz (or < 0).
+ * Call with rowptr = NULL to query nnz only. */
+long long ab200_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val);
+long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val);
+long long ab200_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double* val);
+/* start vector of SURVEY.md §8(d): resid[i] = 2 u(i0+i) - 1, u = top 53 bits of splitmix64(seed + i) / 2^53 */
+int ab200_fill_hash_f64(long long n, long long i0, unsigned long long seed, double* x);
+/* residual check of arpackSolver.hpp:297-352: out[k] = || A z_k - d_k z_k ||_2 (device z, host d/out) */
+int ab200_residuals_f64(int n, const int* rowptr, const int* col, const double* val, int k, const double* z,
+                        long long ldz, const double* d_host, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,4 +1,5 @@
-"""ctypes binding of the CPU parity oracle (oracle/libref_arpack.so). Test infrastructure only."""
+"""ctypes bindings used by the tests: the CPU parity oracle (oracle/libref_arpack.so), the host-logic test
+double (tests/_build/libab200_hostdouble.so) and the product library (arpack-ng_b200/lib/libarpack_b200.so)."""
 import ctypes as C
 import os
 import subprocess
@@ -69,19 +70,23 @@ class Result(dict):
     __getattr__ = dict.__getitem__
 
 
+def _make_allreduce_cb(allreduce):
+    def _ar(user, buf, count, is_double, op):
+        arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double if is_double else C.c_float)), (count,))
+        arr[:] = allreduce(arr.copy(), op)
+    return ALLREDUCE_FN(_ar)
+
+
 class Oracle:
     """One 'process' of the reference: SAVE'd state (e.g. the dgetv0 seed) persists across solves."""
+    prefix = "ref_"
 
     def __init__(self, rank=None, nranks=None, allreduce=None):
         self.L = lib()
         self.ctx = C.c_void_p(self.L.ref_ctx_new())
         self._cb = None
         if rank is not None:
-            def _ar(user, buf, count, is_double, op):
-                dt = np.float64 if is_double else np.float32
-                arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double if is_double else C.c_float)), (count,))
-                arr[:] = allreduce(arr.astype(dt), op)
-            self._cb = ALLREDUCE_FN(_ar)
+            self._cb = _make_allreduce_cb(allreduce)
             self.L.ref_ctx_set_comm(self.ctx, rank, nranks, self._cb, None)
 
     def __del__(self):
@@ -90,10 +95,16 @@ class Oracle:
         except Exception:
             pass
 
-    def stats(self):
+    def stats(self, sym=True, dtype=np.float64):
         v = [C.c_int() for _ in range(5)]
         self.L.ref_ctx_stats(self.ctx, *[C.byref(x) for x in v])
         return dict(zip(("nopx", "nbx", "nrorth", "nitref", "nrstrt"), [x.value for x in v]))
+
+    def _fn(self, name):
+        return getattr(self.L, self.prefix + name)
+
+    def _ctxargs(self, p):
+        return (self.ctx,)
 
     def solve(self, op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
               dtype=np.float64, bop=None, rvec=True, sigma=0.0, sigmai=0.0, c_abi_tol=False, ishift=1,
@@ -125,12 +136,12 @@ class Oracle:
             info.value = 1
         ido = C.c_int(0)
         tolv = rt(tol)
-        aupd = getattr(L, f"ref_{p}{fam}aupd")
+        aupd = self._fn(f"{p}{fam}aupd")
         nsteps = 0
         while True:
             if c_abi_tol:
                 tolv = rt(tol)
-            aupd(self.ctx, C.byref(ido), bmat.encode(), n, which.encode(), nev, C.byref(tolv), _p(res, rp), ncv,
+            aupd(*self._ctxargs(p), C.byref(ido), bmat.encode(), n, which.encode(), nev, C.byref(tolv), _p(res, rp), ncv,
                  _p(v, rp), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl,
                  C.byref(info))
             if ido.value in (-1, 1):
@@ -150,7 +161,8 @@ class Oracle:
             else:
                 break
         out = Result(info=info.value, iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v.copy(),
-                     resid=res.copy(), nconv=int(iparam[4]), stats=self.stats(), tol_eff=tolv.value)
+                     resid=res.copy(), nconv=int(iparam[4]), stats=self.stats(sym, dt), tol_eff=tolv.value,
+                     nsteps=nsteps)
         if info.value < 0 or not eupd:
             return out
         select = np.zeros(ncv, dtype=np.int32)
@@ -159,8 +171,8 @@ class Oracle:
         if sym:
             d = np.zeros(nev, dtype=dt)
             z = np.zeros((nev, n), dtype=dt)
-            L_ = getattr(L, f"ref_{p}seupd")
-            L_(self.ctx, int(rvec), b"A", _p(select, c_int_p), _p(d, rp), _p(z, rp), n, rt(sigma), bmat.encode(), n,
+            L_ = self._fn(f"{p}seupd")
+            L_(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), _p(d, rp), _p(z, rp), n, rt(sigma), bmat.encode(), n,
                which.encode(), nev, rt(tol_e), _p(res, rp), ncv, _p(v, rp), ldv, _p(iparam, c_int_p),
                _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl, C.byref(ierr))
             out.update(d=d, z=z, ierr=ierr.value)
@@ -169,11 +181,92 @@ class Oracle:
             di = np.zeros(nev + 1, dtype=dt)
             z = np.zeros((max(ncv, nev + 1), n), dtype=dt)  # dneupd.f:893 treats Z as n x ncv
             workev = np.zeros(3 * ncv, dtype=dt)
-            L_ = getattr(L, f"ref_{p}neupd")
-            L_(self.ctx, int(rvec), b"A", _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
+            L_ = self._fn(f"{p}neupd")
+            L_(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
                rt(sigmai), _p(workev, rp), bmat.encode(), n, which.encode(), nev, rt(tol_e), _p(res, rp), ncv,
                _p(v, rp), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl,
                C.byref(ierr))
             out.update(dr=dr, di=di, z=z, ierr=ierr.value)
         out.update(workl_eupd=workl.copy(), v_eupd=v.copy(), ipntr_eupd=ipntr.copy(), select=select.copy())
         return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# host-logic test double: the product's host control code over a plain-loop VecOps (no GPU, no oracle)
+# ----------------------------------------------------------------------------------------------------
+_HD_SO = os.path.join(_ROOT, "tests", "_build", "libab200_hostdouble.so")
+_hd = None
+
+
+def build_hostdouble():
+    import glob
+    import scipy
+    os.makedirs(os.path.dirname(_HD_SO), exist_ok=True)
+    src = os.path.join(_ROOT, "tests", "hostdouble", "hostdouble.cpp")
+    deps = [src] + glob.glob(os.path.join(_ROOT, "arpack-ng_b200", "csrc", "*.hpp"))
+    if os.path.exists(_HD_SO) and all(os.path.getmtime(_HD_SO) >= os.path.getmtime(d) for d in deps):
+        return
+    blas = os.path.abspath(glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs",
+                                                  "libscipy_openblas*.so"))[0])
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _HD_SO, src, blas,
+                           "-Wl,-rpath," + os.path.dirname(blas)])
+
+
+def hostdouble_lib():
+    global _hd
+    if _hd is None:
+        build_hostdouble()
+        L = C.CDLL(_HD_SO)
+        L.hd_new.restype = C.c_void_p
+        L.hd_new.argtypes = [C.c_int]
+        L.hd_free.argtypes = [C.c_void_p, C.c_int]
+        L.hd_set_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ALLREDUCE_FN]
+        L.hd_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p]
+        for p, rp, rt in (("d", c_dbl_p, C.c_double), ("s", c_flt_p, C.c_float)):
+            for fam in ("s", "n"):
+                f = getattr(L, f"hd_{p}{fam}aupd")
+                f.argtypes = [C.c_void_p, c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rp, rp, C.c_int, rp,
+                              C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+                f.restype = None
+            f = getattr(L, f"hd_{p}seupd")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, rp, rp, C.c_int, rt, C.c_char_p, C.c_int,
+                          C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp, C.c_int, c_int_p]
+            f.restype = None
+            f = getattr(L, f"hd_{p}neupd")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, rp, rp, rp, C.c_int, rt, rt, rp, C.c_char_p,
+                          C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
+                          C.c_int, c_int_p]
+            f.restype = None
+        _hd = L
+    return _hd
+
+
+class HostDouble(Oracle):
+    """The product's IrlSym/IrlNonsym driven through the plain-loop VecOps test double."""
+    prefix = "hd_"
+
+    def __init__(self, rank=None, nranks=None, allreduce=None):
+        self.L = hostdouble_lib()
+        self._procs = {True: C.c_void_p(self.L.hd_new(1)), False: C.c_void_p(self.L.hd_new(0))}
+        self._cb = None
+        if rank is not None:
+            self._cb = _make_allreduce_cb(allreduce)
+            for isd, pr in self._procs.items():
+                self.L.hd_set_comm(pr, int(isd), rank, nranks, self._cb)
+
+    def __del__(self):
+        try:
+            for isd, pr in self._procs.items():
+                self.L.hd_free(pr, int(isd))
+        except Exception:
+            pass
+
+    def _ctxargs(self, p):
+        return (self._procs[p == "d"],)
+
+    def stats(self, sym=True, dtype=np.float64):
+        out = np.zeros(5, dtype=np.int32)
+        isd = np.dtype(dtype) == np.float64
+        self.L.hd_stats(self._procs[isd], int(isd), int(sym), _p(out, c_int_p))
+        return dict(zip(("nopx", "nbx", "nrorth", "nitref", "nrstrt"), [int(x) for x in out]))

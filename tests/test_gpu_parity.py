@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libarpack_b200.so) against the CPU oracle on the
+same seeded inputs.  Floating-point tolerances are north_star's: eigenvalues 1e-10 relative (FP64) / 1e-4 (FP32),
+||A x - lambda x|| <= tol*||A||; convergence counts (nconv, restarts, OP*x, re-orth steps) identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from backends import Oracle, lib as oracle_lib
+from problems import convdiff2d, dssimp_av, dssimp_exact, laplace2d, laplace3d
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-10  # north_star: converged eigenvalues agree to 1e-10 relative in FP64
+RTOL32 = 1e-4   # ... 1e-4 in FP32
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import arpack_ng_b200 as m
+    m.lib()
+    return m
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _counts(r):
+    return int(r.nconv), int(r.iparam[2]), int(r.iparam[8]), int(r.iparam[10])
+
+
+# --------------------------------------------------------------------------------------------------
+# known-answer tests of the reference, run through the C-ABI
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("host_buffers", [False, True])
+def test_icb_arpack_c_diag(ab, host_buffers):
+    """TESTS/icb_arpack_c.c:31-91: A = diag(1..1000), nev=9, ncv=19, 'LM', tol=1e-6 -> d = 992..1000 (1e-5)."""
+    torch = _torch()
+    n = 1000
+    if host_buffers:
+        diag = np.arange(1, n + 1, dtype=np.float64)
+
+        def op(x, y, *_):
+            y[:] = diag * x
+    else:
+        diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+
+        def op(x, y, *_):
+            torch.mul(diag, x, out=y)
+    r = ab.solve(op, n, 9, 19, "LM", tol=1e-6, mxiter=10000, host_buffers=host_buffers)
+    assert r.info == 0 and r.ierr == 0
+    assert r.nconv >= 9
+    assert np.abs(r.d - np.arange(992, 1001)).max() < 1e-5
+    ref = Oracle().solve(lambda x: np.arange(1, n + 1) * x, n, 9, 19, "LM", tol=1e-6, mxiter=10000, c_abi_tol=True)
+    assert _counts(r) == _counts(ref)
+
+
+def test_bug_1315_double(ab):
+    """TESTS/bug_1315_double.c:23-84: dnaupd_c/dneupd_c on the same matrix, tol=0 -> dr[i] = 1000-i (1e-6)."""
+    torch = _torch()
+    n = 1000
+    diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+    r = ab.solve(lambda x, y, *_: torch.mul(diag, x, out=y), n, 9, 19, "LM", sym=False, tol=0.0, mxiter=10 * n)
+    assert r.info == 0 and r.ierr == 0
+    assert np.abs(r.dr[:9] - (1000 - np.arange(9))).max() < 1e-6
+    assert np.abs(r.di[:9]).max() == 0.0
+
+
+def test_bug_1315_single(ab):
+    """TESTS/bug_1315_single.c:75: float twin, 1e-1."""
+    torch = _torch()
+    n = 1000
+    diag = torch.arange(1, n + 1, dtype=torch.float32, device="cuda")
+    r = ab.solve(lambda x, y, *_: torch.mul(diag, x, out=y), n, 9, 19, "LM", sym=False, tol=0.0, mxiter=10 * n,
+                 dtype=np.float32)
+    assert r.info == 0 and r.ierr == 0
+    assert np.abs(r.dr[:9] - (1000 - np.arange(9))).max() < 1e-1
+
+
+def test_dssimp_config1(ab):
+    """BASELINE config 1 = EXAMPLES/SIMPLE/dssimp.f: nx=10, nev=4, ncv=20, 'LM', tol=0, mxiter=300, random start
+    from the LAPACK dlarnv stream (info=0).  The spectrum has a double eigenvalue (919.78...), so restart counts are
+    rounding-sensitive; the eigenvalues themselves are pinned by the analytic spectrum."""
+    torch = _torch()
+    nx = 10
+    A = ab.CsrOperator.laplace2d(nx, nx, scale=float((nx + 1) ** 2))
+    r = ab.solve(A, nx * nx, 4, 20, "LM", tol=0.0, mxiter=300)
+    assert r.info == 0 and r.ierr == 0 and r.nconv == 4
+    exact = dssimp_exact(nx, 4)
+    assert np.abs(r.d - exact).max() / exact.max() < 1e-12
+    rn = A.residuals(r.d, r.z, nx * nx)
+    assert (rn / np.abs(r.d) < 1e-10).all()
+
+
+def test_first_handoff_is_the_dlarnv_stream(ab):
+    """dgetv0.f:236 draws the start vector from LAPACK dlarnv(idist=2, iseed={1,3,5,7}); the CUDA generator must
+    reproduce that stream bit for bit (first hand-off: x = workd(ipntr(1)) = the random vector)."""
+    torch = _torch()
+    L = ab.lib()
+    L.ab200_reset_seed()
+    n, nev, ncv = 5000, 3, 12
+    workl = np.zeros(ncv * ncv + 8 * ncv)
+    iparam = np.zeros(11, dtype=np.int32)
+    iparam[[0, 2, 3, 6]] = [1, 10, 1, 1]
+    ipntr = np.zeros(14, dtype=np.int32)
+    ido = np.zeros(1, dtype=np.int32)
+    info = np.zeros(1, dtype=np.int32)
+    resid = torch.zeros(n, dtype=torch.float64, device="cuda")
+    v = torch.zeros(n * ncv, dtype=torch.float64, device="cuda")
+    workd = torch.zeros(3 * n, dtype=torch.float64, device="cuda")
+    ab.dsaupd_c(ido, "I", n, "LM", nev, 0.0, resid, ncv, v, n, iparam, ipntr, workd, workl, info)
+    assert ido[0] == -1 and ipntr[0] == 1 and ipntr[1] == n + 1
+    x = workd[:n].cpu().numpy()
+    seed = np.array([1, 3, 5, 7], dtype=np.int32)
+    ref = np.zeros(n)
+    oracle_lib().ref_dlarnv2(seed.ctypes.data_as(C.POINTER(C.c_int)), n, ref.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(x, ref)
+    assert abs(ref[0] - 0.3957424639187579) < 1e-16  # SURVEY.md §8c golden value
+    L.ab200_release(workl.ctypes.data)
+    L.ab200_reset_seed()
+
+
+# --------------------------------------------------------------------------------------------------
+# oracle parity on seeded inputs (info = 1, hashed start vector)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny,nev,ncv,which", [(48, 40, 6, 24, "LA"), (33, 29, 5, 20, "SA"), (64, 37, 8, 30, "LM"),
+                                                   (25, 31, 4, 16, "BE")])
+@pytest.mark.parametrize("mode", ["auto", "generic"])
+def test_laplace2d_vs_oracle(ab, nx, ny, nev, ncv, which, mode):
+    L = ab.lib()
+    L.ab200_set_kernel_mode(0 if mode == "auto" else 1)
+    try:
+        A = ab.CsrOperator.laplace2d(nx, ny)
+        n = A.n
+        As = laplace2d(nx, ny)
+        assert (abs(A.to_scipy() - As)).max() == 0.0
+        r0 = ab.hashed_start_vector_numpy(n)
+        assert np.array_equal(ab.hashed_start_vector(n).cpu().numpy(), r0)
+        r = ab.solve(A, n, nev, ncv, which, tol=1e-10, mxiter=2000, resid=r0)
+        ref = Oracle().solve(lambda x: As @ x, n, nev, ncv, which, tol=1e-10, mxiter=2000, resid=r0)
+        assert r.info == ref.info == 0 and r.ierr == 0
+        assert _counts(r) == _counts(ref)
+        assert np.abs(r.d - ref.d).max() / np.abs(ref.d).max() < RTOL64
+        rn = A.residuals(r.d, r.z, n)
+        assert (rn <= 1e-10 * 8.0 * 10).all()
+    finally:
+        L.ab200_set_kernel_mode(0)
+
+
+def test_laplace2d_host_buffers_match_device_buffers(ab):
+    """The host-pointer path (unmodified CPU caller) and the device-pointer path run the same kernels."""
+    nx, ny, nev, ncv = 40, 36, 5, 20
+    A = ab.CsrOperator.laplace2d(nx, ny)
+    r0 = ab.hashed_start_vector_numpy(A.n)
+    rd = ab.solve(A, A.n, nev, ncv, "LA", tol=1e-10, mxiter=1000, resid=r0)
+    rh = ab.solve(A, A.n, nev, ncv, "LA", tol=1e-10, mxiter=1000, resid=r0, host_buffers=True)
+    assert _counts(rd) == _counts(rh)
+    assert np.array_equal(rd.d, rh.d)
+    assert np.allclose(rd.z[:A.n * nev].cpu().numpy(), rh.z[:A.n * nev], rtol=0, atol=1e-12)
+
+
+def test_convdiff_nonsym_vs_oracle(ab):
+    """BASELINE config 4 (dndrv1-style) at a size the oracle finishes: dnaupd nev=6 ncv=30 'LR'."""
+    nx, nev, ncv = 40, 6, 30
+    A = ab.CsrOperator.convdiff2d(nx, 100.0)
+    As = convdiff2d(nx, 100.0)
+    assert abs(A.to_scipy() - As).max() < 1e-9
+    As = A.to_scipy()
+    r0 = ab.hashed_start_vector_numpy(A.n)
+    r = ab.solve(A, A.n, nev, ncv, "LR", sym=False, tol=1e-10, mxiter=2000, resid=r0)
+    ref = Oracle().solve(lambda x: As @ x, A.n, nev, ncv, "LR", sym=False, tol=1e-10, mxiter=2000, resid=r0)
+    assert r.info == ref.info == 0 and r.ierr == ref.ierr == 0
+    assert _counts(r) == _counts(ref)
+    lam, lam_ref = r.dr[:r.nconv] + 1j * r.di[:r.nconv], ref.dr[:ref.nconv] + 1j * ref.di[:ref.nconv]
+    assert np.abs(np.sort_complex(lam) - np.sort_complex(lam_ref)).max() / np.abs(lam_ref).max() < RTOL64
+
+
+def test_float32_sym_vs_oracle(ab):
+    nx, ny, nev, ncv = 30, 26, 4, 16
+    A64 = laplace2d(nx, ny)
+    torch = _torch()
+    A = ab.CsrOperator.from_scipy(A64)
+    valf = A.val.float()
+    n = A.n
+    L = ab.lib()
+
+    def op(x, y, *_):
+        assert L.ab200_csr_spmv_f32(n, A.rowptr.data_ptr(), A.col.data_ptr(), valf.data_ptr(), x.data_ptr(),
+                                    y.data_ptr()) == 0
+    r0 = ab.hashed_start_vector_numpy(n).astype(np.float32)
+    r = ab.solve(op, n, nev, ncv, "LA", tol=1e-5, mxiter=2000, resid=r0, dtype=np.float32)
+    A32 = A64.astype(np.float32)
+    ref = Oracle().solve(lambda x: A32 @ x, n, nev, ncv, "LA", tol=1e-5, mxiter=2000, resid=r0, dtype=np.float32)
+    assert r.info == 0 and r.ierr == 0
+    assert np.abs(r.d - ref.d).max() / np.abs(ref.d).max() < RTOL32
+    assert r.nconv == ref.nconv
+
+
+def test_laplace3d_generator_and_spmv(ab):
+    torch = _torch()
+    nx, ny, nz = 7, 5, 6
+    A = ab.CsrOperator.laplace3d(nx, ny, nz)
+    As = laplace3d(nx, ny, nz)
+    assert abs(A.to_scipy() - As).max() == 0.0
+    x = torch.randn(A.n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    A(x, y)
+    assert np.allclose(y.cpu().numpy(), As @ x.cpu().numpy(), rtol=1e-13, atol=1e-13)
+
+
+def test_kernels_counted(ab):
+    st = ab.launch_stats()
+    assert st["kernels"] > 0
