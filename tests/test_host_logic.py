@@ -1,0 +1,310 @@
+"""CPU tests of the product's HOST logic: arpack-ng_b200/csrc/irl_*.hpp (state machine, ncv-sized math, error
+codes, PARPACK semantics) driven through the plain-loop VecOps test double (tests/hostdouble) and compared with the
+oracle.  No CUDA kernel runs here; the kernels are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from backends import HostDouble, Oracle
+from problems import convdiff2d, dssimp_av, dssimp_exact, laplace2d
+from test_oracle_golden import LogicalRanks, split_rows
+
+
+def counts(r):
+    return int(r.nconv), int(r.iparam[2]), int(r.iparam[8]), int(r.iparam[9]), int(r.iparam[10]), r.stats["nitref"], \
+        r.stats["nrstrt"]
+
+
+def start(n, seed=7):
+    return np.random.default_rng(seed).uniform(-1, 1, n)
+
+
+@pytest.mark.parametrize("which", ["LA", "SA", "LM", "SM", "BE"])
+def test_sym_matches_oracle(which):
+    nx, ny, nev, ncv = 17, 13, 5, 18
+    A = laplace2d(nx, ny)
+    n = nx * ny
+    r0 = start(n)
+    a = HostDouble().solve(lambda x: A @ x, n, nev, ncv, which, tol=1e-10, mxiter=3000, resid=r0)
+    b = Oracle().solve(lambda x: A @ x, n, nev, ncv, which, tol=1e-10, mxiter=3000, resid=r0)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert counts(a) == counts(b)
+    assert np.abs(a.d - b.d).max() / np.abs(b.d).max() < 1e-12
+    # Ritz vectors agree up to sign
+    for i in range(nev):
+        assert min(np.linalg.norm(a.z[i] - b.z[i]), np.linalg.norm(a.z[i] + b.z[i])) < 1e-7
+    # workl after *eupd: Ritz values (ipntr(8)) and error bounds (ipntr(9)) as dseupd.f:356-412 documents
+    ihd, ihb = a.ipntr_eupd[7] - 1, a.ipntr_eupd[8] - 1
+    assert np.allclose(a.workl_eupd[ihd:ihd + nev], b.workl_eupd[ihd:ihd + nev], rtol=1e-12)
+    assert np.allclose(a.workl_eupd[ihb:ihb + nev], b.workl_eupd[ihb:ihb + nev], rtol=1e-3, atol=1e-18)
+
+
+def test_sym_fixed_restart_budget_state_matches():
+    """with a fixed restart budget (expect info=1) H, Ritz values and bounds must agree."""
+    nx, ny, nev, ncv = 40, 33, 6, 20
+    A = laplace2d(nx, ny)
+    n = nx * ny
+    r0 = start(n, 3)
+    a = HostDouble().solve(lambda x: A @ x, n, nev, ncv, "LA", tol=1e-12, mxiter=3, resid=r0, eupd=False)
+    b = Oracle().solve(lambda x: A @ x, n, nev, ncv, "LA", tol=1e-12, mxiter=3, resid=r0, eupd=False)
+    assert a.info == b.info == 1
+    assert counts(a) == counts(b)
+    ih, ritz, bnd = a.ipntr[4] - 1, a.ipntr[5] - 1, a.ipntr[6] - 1
+    assert np.allclose(a.workl[ih:ih + 2 * ncv], b.workl[ih:ih + 2 * ncv], rtol=1e-9, atol=1e-11)
+    assert np.allclose(a.workl[ritz:ritz + ncv], b.workl[ritz:ritz + ncv], rtol=1e-11)
+    assert np.allclose(a.workl[bnd:bnd + ncv], b.workl[bnd:bnd + ncv], rtol=1e-5, atol=1e-14)
+
+
+def test_dssimp_eigenvalues():
+    nx = 10
+    r = HostDouble().solve(dssimp_av(nx), nx * nx, 4, 20, "LM", tol=0.0, mxiter=300)
+    assert r.info == 0 and r.ierr == 0 and r.nconv == 4
+    assert np.abs(r.d - dssimp_exact(nx, 4)).max() < 1e-10
+
+
+@pytest.mark.parametrize("which", ["LM", "SM", "LR", "SR"])  # real simple spectrum: LI/SI would be all ties
+def test_nonsym_matches_oracle(which):
+    nx, nev, ncv = 12, 4, 16
+    A = convdiff2d(nx, 7.0)
+    n = nx * nx
+    r0 = start(n, 11)
+    a = HostDouble().solve(lambda x: A @ x, n, nev, ncv, which, sym=False, tol=1e-10, mxiter=3000, resid=r0)
+    b = Oracle().solve(lambda x: A @ x, n, nev, ncv, which, sym=False, tol=1e-10, mxiter=3000, resid=r0)
+    assert a.info == b.info and a.ierr == b.ierr == 0
+    assert counts(a) == counts(b)
+    la, lb = a.dr[:a.nconv] + 1j * a.di[:a.nconv], b.dr[:b.nconv] + 1j * b.di[:b.nconv]
+    assert np.abs(la - lb).max() / np.abs(lb).max() < 1e-10
+    for i in range(a.nconv):
+        assert min(np.linalg.norm(a.z[i] - b.z[i]), np.linalg.norm(a.z[i] + b.z[i])) < 1e-6
+
+
+@pytest.mark.parametrize("which", ["LM", "LI", "SR"])
+def test_nonsym_complex_pairs(which):
+    """Complex conjugate Ritz pairs: double-shift sweeps (dnapps.f:455-530), pair-preserving selection
+    (dngets.f:191-195), complex eigenvector handling in dneupd."""
+    rng = np.random.default_rng(5)
+    n = 120
+    A = rng.standard_normal((n, n)) / np.sqrt(n) + np.diag(np.linspace(0, 3, n))
+    r0 = start(n, 2)
+    a = HostDouble().solve(lambda x: A @ x, n, 5, 24, which, sym=False, tol=1e-10, mxiter=3000, resid=r0)
+    b = Oracle().solve(lambda x: A @ x, n, 5, 24, which, sym=False, tol=1e-10, mxiter=3000, resid=r0)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert counts(a) == counts(b)
+    la, lb = a.dr[:a.nconv] + 1j * a.di[:a.nconv], b.dr[:b.nconv] + 1j * b.di[:b.nconv]
+    assert np.abs(la - lb).max() < 1e-9
+    ev = np.linalg.eigvals(A)
+    k = 0
+    while k < a.nconv:
+        assert np.abs(ev - la[k]).min() < 1e-8
+        if a.di[k] != 0:
+            x = a.z[k] + 1j * a.z[k + 1]
+            assert np.linalg.norm(A @ x - la[k] * x) < 1e-8
+            k += 2
+        else:
+            assert np.linalg.norm(A @ a.z[k] - a.dr[k] * a.z[k]) < 1e-8
+            k += 1
+
+
+def test_float32_matches_oracle():
+    nx, ny, nev, ncv = 15, 12, 4, 14
+    A = laplace2d(nx, ny).astype(np.float32)
+    n = nx * ny
+    r0 = start(n).astype(np.float32)
+    a = HostDouble().solve(lambda x: A @ x, n, nev, ncv, "LA", tol=1e-5, mxiter=3000, resid=r0, dtype=np.float32)
+    b = Oracle().solve(lambda x: A @ x, n, nev, ncv, "LA", tol=1e-5, mxiter=3000, resid=r0, dtype=np.float32)
+    assert a.info == b.info == 0 and a.nconv == b.nconv
+    assert np.abs(a.d - b.d).max() / np.abs(b.d).max() < 1e-4
+
+
+def test_generalized_and_shift_invert_modes():
+    """(f)-row functionality: bmat='G' hand-offs (ido=2), modes 2 and 3, purification (dseupd.f:840-857)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    n = 100
+    A = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tocsc()
+    M = sp.diags([np.ones(n - 1) / 6, 4 * np.ones(n) / 6, np.ones(n - 1) / 6], [-1, 0, 1]).tocsc()
+    lu = sla.splu(A)
+    lu2 = sla.splu(A.tocsc())
+    luM = sla.splu(M)
+    r0 = start(n, 4)
+    cases = [
+        dict(op=lambda x: lu.solve(x), mode=3, bmat="I", sigma=0.0, bop=None),
+        dict(op=lambda x, is_bx=False: lu2.solve(x if is_bx else M @ x), mode=3, bmat="G", sigma=0.0,
+             bop=lambda x: M @ x),
+        dict(op=lambda x: (luM.solve(A @ x), A @ x), mode=2, bmat="G", sigma=0.0, bop=lambda x: M @ x),
+    ]
+    for c in cases:
+        a = HostDouble().solve(c["op"], n, 4, 12, "LM", tol=1e-12, mxiter=500, mode=c["mode"], bmat=c["bmat"],
+                               sigma=c["sigma"], bop=c["bop"], resid=r0)
+        b = Oracle().solve(c["op"], n, 4, 12, "LM", tol=1e-12, mxiter=500, mode=c["mode"], bmat=c["bmat"],
+                           sigma=c["sigma"], bop=c["bop"], resid=r0)
+        assert a.info == b.info == 0 and a.ierr == b.ierr == 0, c
+        assert counts(a) == counts(b), c
+        assert np.abs(a.d - b.d).max() / np.abs(b.d).max() < 1e-11
+        for i in range(4):
+            assert min(np.linalg.norm(a.z[i] - b.z[i]), np.linalg.norm(a.z[i] + b.z[i])) < 1e-7
+
+
+def test_user_supplied_shifts_ido3():
+    """ishift = 0: the RCI returns ido=3 and reads np shifts from workl(ipntr(11)) (dsaup2.f:713-743)."""
+    import ctypes as C
+    nx, ny, nev, ncv = 12, 9, 3, 12
+    A = laplace2d(nx, ny)
+    n = nx * ny
+
+    def run(cls):
+        o = cls()
+        L, p = o.L, "d"
+        v = np.zeros((ncv, n)); workd = np.zeros(3 * n); workl = np.zeros(ncv * ncv + 8 * ncv)
+        iparam = np.zeros(11, dtype=np.int32); ipntr = np.zeros(14, dtype=np.int32)
+        iparam[[0, 2, 3, 6]] = [0, 200, 1, 1]
+        ido = C.c_int(0); info = C.c_int(1); tol = C.c_double(1e-10)
+        resid = start(n, 9)
+        aupd = o._fn("dsaupd")
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        n3 = 0
+        while True:
+            aupd(*o._ctxargs(p), C.byref(ido), b"I", n, b"LA", nev, C.byref(tol), dp(resid), ncv, dp(v), n, ip(iparam),
+                 ip(ipntr), dp(workd), dp(workl), len(workl), C.byref(info))
+            if ido.value in (-1, 1):
+                workd[ipntr[1] - 1:ipntr[1] - 1 + n] = A @ workd[ipntr[0] - 1:ipntr[0] - 1 + n]
+            elif ido.value == 3:
+                npsh = iparam[7]
+                ritz = workl[ipntr[5] - 1:ipntr[5] - 1 + ncv]
+                # exact shifts supplied by hand: the np unwanted Ritz values (smallest for 'LA')
+                workl[ipntr[10] - 1:ipntr[10] - 1 + npsh] = np.sort(ritz)[:npsh]
+                n3 += 1
+            else:
+                break
+        return info.value, iparam.copy(), workl[ipntr[5] - 1:ipntr[5] - 1 + nev].copy(), n3
+    a, b = run(HostDouble), run(Oracle)
+    assert a[0] == b[0] == 0 and a[3] == b[3] > 0
+    assert np.array_equal(a[1], b[1])
+    assert np.allclose(a[2], b[2], rtol=1e-12)
+    ev = np.sort(np.linalg.eigvalsh(A.toarray()))
+    assert np.abs(np.sort(a[2]) - ev[-nev:]).max() < 1e-8
+
+
+@pytest.mark.parametrize("kw,expect", [
+    (dict(n=0), -1), (dict(nev=0), -2), (dict(ncv=3, nev=3), -3), (dict(ncv=200), -3), (dict(mxiter=0), -4),
+    (dict(which="XX"), -5), (dict(bmat="X"), -6), (dict(lworkl_short=True), -7), (dict(mode=6), -10),
+    (dict(mode=1, bmat="G"), -11), (dict(ishift=2), -12), (dict(nev=1, which="BE", ncv=5), -13)])
+def test_sym_argument_errors_match_reference(kw, expect):
+    """dsaupd.f:501-543: argument errors come back as info<0 with ido=99, never an abort."""
+    import ctypes as C
+    base = dict(n=100, nev=3, ncv=10, which="LM", bmat="I", mode=1, ishift=1, mxiter=10)
+    base.update({k: v for k, v in kw.items() if k != "lworkl_short"})
+    for cls in (HostDouble, Oracle):
+        o = cls()
+        n, nev, ncv = base["n"], base["nev"], base["ncv"]
+        nn = max(n, 1)
+        lworkl = ncv * ncv + 8 * ncv - (1 if kw.get("lworkl_short") else 0)
+        v = np.zeros(nn * ncv); workd = np.zeros(3 * nn); workl = np.zeros(ncv * ncv + 8 * ncv)
+        resid = np.zeros(nn)
+        iparam = np.zeros(11, dtype=np.int32); ipntr = np.zeros(14, dtype=np.int32)
+        iparam[[0, 2, 3, 6]] = [base["ishift"], base["mxiter"], 1, base["mode"]]
+        ido = C.c_int(0); info = C.c_int(0); tol = C.c_double(0.0)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        o._fn("dsaupd")(*o._ctxargs("d"), C.byref(ido), base["bmat"].encode(), n, base["which"].encode(), nev,
+                        C.byref(tol), dp(resid), ncv, dp(v), nn, ip(iparam), ip(ipntr), dp(workd), dp(workl), lworkl,
+                        C.byref(info))
+        assert ido.value == 99 and info.value == expect, (cls.__name__, info.value)
+
+
+@pytest.mark.parametrize("kw,expect", [
+    (dict(ncv=4, nev=3), -3), (dict(which="LA"), -5), (dict(mode=5), -10), (dict(lworkl_short=True), -7)])
+def test_nonsym_argument_errors_match_reference(kw, expect):
+    import ctypes as C
+    base = dict(n=100, nev=3, ncv=10, which="LM", bmat="I", mode=1, ishift=1, mxiter=10)
+    base.update({k: v for k, v in kw.items() if k != "lworkl_short"})
+    for cls in (HostDouble, Oracle):
+        o = cls()
+        n, nev, ncv = base["n"], base["nev"], base["ncv"]
+        lworkl = 3 * ncv * ncv + 6 * ncv - (1 if kw.get("lworkl_short") else 0)
+        v = np.zeros(n * ncv); workd = np.zeros(3 * n); workl = np.zeros(3 * ncv * ncv + 6 * ncv); resid = np.zeros(n)
+        iparam = np.zeros(11, dtype=np.int32); ipntr = np.zeros(14, dtype=np.int32)
+        iparam[[0, 2, 3, 6]] = [base["ishift"], base["mxiter"], 1, base["mode"]]
+        ido = C.c_int(0); info = C.c_int(0); tol = C.c_double(0.0)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        o._fn("dnaupd")(*o._ctxargs("d"), C.byref(ido), base["bmat"].encode(), n, base["which"].encode(), nev,
+                        C.byref(tol), dp(resid), ncv, dp(v), n, ip(iparam), ip(ipntr), dp(workd), dp(workl), lworkl,
+                        C.byref(info))
+        assert ido.value == 99 and info.value == expect, (cls.__name__, info.value)
+
+
+def test_invariant_subspace_restart():
+    """Start vector inside a 3-dimensional invariant subspace: the factorisation breaks down (rnorm = 0) and the
+    reference regenerates a vector with dgetv0 (dsaitr.f:378-427, nrstrt > 0)."""
+    n = 60
+    diag = np.arange(1, n + 1, dtype=float)
+    r0 = np.zeros(n)
+    r0[[3, 17, 41]] = [1.0, -2.0, 0.5]
+    a = HostDouble().solve(lambda x: diag * x, n, 4, 12, "LM", tol=1e-10, mxiter=500, resid=r0)
+    b = Oracle().solve(lambda x: diag * x, n, 4, 12, "LM", tol=1e-10, mxiter=500, resid=r0)
+    assert b.stats["nrstrt"] > 0
+    assert a.info == b.info and a.stats["nrstrt"] == b.stats["nrstrt"]
+    assert a.nconv == b.nconv
+    assert np.abs(np.sort(a.d) - np.sort(b.d)).max() < 1e-8
+
+
+def test_max_iterations_info_1():
+    nx, ny = 30, 29
+    A = laplace2d(nx, ny)
+    r0 = start(nx * ny)
+    for cls in (HostDouble, Oracle):
+        r = cls().solve(lambda x: A @ x, nx * ny, 6, 14, "SA", tol=1e-14, mxiter=2, resid=r0, eupd=False)
+        assert r.info == 1 and int(r.iparam[2]) == 3
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_parpack_semantics_match_oracle(nranks):
+    """pdsaupd/pdseupd path of the host logic (per-rank seeds, no initial OP*x, fused all-reduces) against the
+    oracle's PARPACK mode, both on P logical ranks; the known answer is icb_parpack_c.c's 992..1000."""
+    N = 1000
+    cnts, offs = split_rows(N, nranks)
+
+    def run(cls):
+        world = LogicalRanks(nranks)
+
+        def rank_main(r, ar):
+            diag = np.arange(offs[r] + 1, offs[r + 1] + 1, dtype=float)
+            return cls(rank=r, nranks=nranks, allreduce=ar).solve(lambda x: diag * x, cnts[r], 9, 19, "LM", tol=1e-6,
+                                                                   mxiter=10000, c_abi_tol=True)
+        return world.run(rank_main)
+    a, b = run(HostDouble), run(Oracle)
+    for ra, rb in zip(a, b):
+        assert ra.info == rb.info == 0 and ra.ierr == rb.ierr == 0
+        assert np.abs(ra.d - np.arange(992, 1001)).max() < 1e-5
+        assert counts(ra) == counts(rb)
+        assert np.abs(ra.d - rb.d).max() < 1e-9
+
+
+def test_parpack_nonsym_semantics_match_oracle():
+    nranks = 2
+    nx = 14
+    A = convdiff2d(nx, 5.0).tocsr()
+    n = nx * nx
+    cnts, offs = split_rows(n, nranks)
+    r0 = start(n, 21)
+
+    def run(cls):
+        world = LogicalRanks(nranks)
+        xs = [None] * nranks
+
+        def rank_main(r, ar):
+            def op(x):
+                # "halo exchange": gather the full vector through the all-reduce callback
+                full = np.zeros(n)
+                full[offs[r]:offs[r + 1]] = x
+                full = ar(full, 0)
+                return (A @ full)[offs[r]:offs[r + 1]]
+            return cls(rank=r, nranks=nranks, allreduce=ar).solve(op, cnts[r], 4, 16, "LM", sym=False, tol=1e-10,
+                                                                   mxiter=2000, resid=r0[offs[r]:offs[r + 1]])
+        return world.run(rank_main)
+    a, b = run(HostDouble), run(Oracle)
+    for ra, rb in zip(a, b):
+        assert ra.info == rb.info == 0
+        assert counts(ra) == counts(rb)
+        assert np.abs(ra.dr - rb.dr).max() / np.abs(rb.dr).max() < 1e-10
