@@ -87,6 +87,10 @@ def lib():
     L.ab200_release.argtypes = [vp]
     L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.ab200_device_count.restype = C.c_int
+    L.ab200_profile_enable.argtypes = [C.c_int]
+    L.ab200_profile_get.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
+                                    C.POINTER(C.c_double)]
+    L.ab200_profile_get.restype = C.c_int
     L.ab200_version.restype = C.c_char_p
     L.ab200_nccl_unique_id.argtypes = [vp]
     L.ab200_comm_create.argtypes = [vp, C.c_int, C.c_int]
@@ -97,7 +101,7 @@ def lib():
     L.ab200_csr_spmv_halo_f64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     L.ab200_gen_laplace2d.argtypes = [C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.ab200_gen_laplace2d.restype = C.c_longlong
-    L.ab200_gen_laplace3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.ab200_gen_laplace3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp]
     L.ab200_gen_laplace3d.restype = C.c_longlong
     L.ab200_gen_convdiff2d.argtypes = [C.c_int, C.c_double, vp, vp, vp]
     L.ab200_gen_convdiff2d.restype = C.c_longlong
@@ -111,6 +115,23 @@ def launch_stats():
     out = (C.c_ulonglong * 4)()
     lib().ab200_launch_stats(out)
     return {"kernels": int(out[0]), "allreduces": int(out[1]), "tma_path": int(out[2]), "generic_path": int(out[3])}
+
+
+def profile(enable=None, reset=False):
+    """Per-kernel CUDA-event timings accumulated by the library: {name: {launches, ms, bytes}}."""
+    L = lib()
+    if reset:
+        L.ab200_profile_reset()
+    if enable is not None:
+        L.ab200_profile_enable(int(enable))
+    out = {}
+    name = C.create_string_buffer(64)
+    ms, ln, by = C.c_double(), C.c_ulonglong(), C.c_double()
+    cnt = L.ab200_profile_get(-1, name, C.byref(ms), C.byref(ln), C.byref(by))
+    for i in range(cnt):
+        L.ab200_profile_get(i, name, C.byref(ms), C.byref(ln), C.byref(by))
+        out[name.value.decode()] = {"launches": int(ln.value), "ms": float(ms.value), "bytes": float(by.value)}
+    return out
 
 
 def _addr(a):
@@ -314,18 +335,18 @@ class CsrOperator:
         return CsrOperator(n, rowptr, col, val)
 
     @staticmethod
-    def laplace3d(nx, ny, nz, z0=0, nzloc=None, device="cuda"):
+    def laplace3d(nx, ny, nz, z0=0, nzloc=None, device="cuda", diag=6.0):
         import torch
         L = lib()
         nzloc = nz if nzloc is None else nzloc
         nloc = nx * ny * nzloc
-        nnz = L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, None, None, None)
+        nnz = L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, diag, None, None, None)
         if nnz < 0:
             raise ArpackB200Error("laplace3d: nnz exceeds int32")
         rowptr = torch.empty(nloc + 1, dtype=torch.int32, device=device)
         col = torch.empty(nnz, dtype=torch.int32, device=device)
         val = torch.empty(nnz, dtype=torch.float64, device=device)
-        if L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, rowptr.data_ptr(), col.data_ptr(), val.data_ptr()) != nnz:
+        if L.ab200_gen_laplace3d(nx, ny, nz, z0, nzloc, diag, rowptr.data_ptr(), col.data_ptr(), val.data_ptr()) != nnz:
             raise ArpackB200Error("laplace3d generator failed")
         op = CsrOperator(nloc, rowptr, col, val)
         op.halo_lo = nx * ny if z0 > 0 else 0

@@ -491,6 +491,18 @@ void ab200_reset_seed(void) {
   Globals<float>::seed = SeedState(); Globals<float>::seed_par = SeedState();
   Globals<double>::smlnum_first = -1.0; Globals<float>::smlnum_first = -1.0f;
 }
+void ab200_profile_enable(int on) { profiler().enabled = (on != 0); }
+void ab200_profile_reset(void) { profiler().reset(); }
+// returns the number of profiled kernels; entry idx (if valid) is copied out
+int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* launches, double* bytes) {
+  const auto& t = profiler().table();
+  if (idx >= 0 && idx < (int)t.size()) {
+    std::strncpy(name64, t[idx].name, 63);
+    name64[63] = 0;
+    *ms = t[idx].ms; *launches = t[idx].launches; *bytes = t[idx].bytes;
+  }
+  return (int)t.size();
+}
 int ab200_device_count(void) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }

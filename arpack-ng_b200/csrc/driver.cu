@@ -57,6 +57,8 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   const double avg = nnz_hint > 0 ? (double)nnz_hint / nrows : 8.0;
   const int threads = 256;
   cudaStream_t s = cur_stream();
+  const long long nnz = nnz_hint > 0 ? nnz_hint : 0;
+  ProfScope ps(s, "csr_spmv", (double)nnz * (sizeof(T) + 4.0) + (nrows + 1) * 4.0 + 2.0 * nrows * sizeof(T));
   auto grid_for = [&](int lpr) {
     long long g = ((long long)nrows * lpr + threads - 1) / threads;
     const long long cap = 148LL * 32;
@@ -158,7 +160,8 @@ __device__ inline long long lap3d_before(long long r, int nx, int ny, int nzloc,
   if (!has_hi) before -= (iz == nzloc - 1 ? rem : 0) + (iz >= nzloc ? plane : 0);
   return before;
 }
-__global__ void k_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val) {
+__global__ void k_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, double diag, int* rowptr, int* col,
+                                double* val) {
   const long long plane = (long long)nx * ny, nloc = plane * nzloc;
   const bool has_lo = z0 > 0, has_hi = (z0 + nzloc) < nz;
   const long long lo_base = nloc, hi_base = nloc + (has_lo ? plane : 0);
@@ -175,7 +178,7 @@ __global__ void k_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* 
     else if (has_lo) { col[p] = (int)(lo_base + rem); val[p] = -1.0; ++p; }
     if (iy > 0) { col[p] = (int)(r - nx); val[p] = -1.0; ++p; }
     if (ix > 0) { col[p] = (int)(r - 1); val[p] = -1.0; ++p; }
-    col[p] = (int)r; val[p] = 6.0; ++p;
+    col[p] = (int)r; val[p] = diag; ++p;
     if (ix < nx - 1) { col[p] = (int)(r + 1); val[p] = -1.0; ++p; }
     if (iy < ny - 1) { col[p] = (int)(r + nx); val[p] = -1.0; ++p; }
     if (iz < nzloc - 1) { col[p] = (int)(r + plane); val[p] = -1.0; ++p; }
@@ -284,7 +287,8 @@ long long ab200_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double
   launch_stats().kernels++;
   return cudaGetLastError() == cudaSuccess ? nnz : -1;
 }
-long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val) {
+long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, double diag, int* rowptr, int* col,
+                              double* val) {
   const long long plane = (long long)nx * ny, nloc = plane * nzloc;
   const bool has_lo = z0 > 0, has_hi = (z0 + nzloc) < nz;
   long long nnz = 7 * nloc - 2LL * ny * nzloc - 2LL * nx * nzloc;
@@ -292,7 +296,7 @@ long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* ro
   if (!has_hi) nnz -= plane;
   if (nnz > 2147483647LL) return -2;
   if (!rowptr) return nnz;
-  k_gen_laplace3d<<<gen_grid(nloc + 1), 256, 0, cur_stream()>>>(nx, ny, nz, z0, nzloc, rowptr, col, val);
+  k_gen_laplace3d<<<gen_grid(nloc + 1), 256, 0, cur_stream()>>>(nx, ny, nz, z0, nzloc, diag, rowptr, col, val);
   launch_stats().kernels++;
   return cudaGetLastError() == cudaSuccess ? nnz : -1;
 }

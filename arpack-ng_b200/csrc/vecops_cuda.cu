@@ -19,6 +19,55 @@ LaunchStats& launch_stats() {
   return s;
 }
 
+Profiler& profiler() {
+  static Profiler p;
+  return p;
+}
+cudaEvent_t Profiler::get_event() {
+  if (!pool_.empty()) {
+    cudaEvent_t e = pool_.back();
+    pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  AB200_CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+void Profiler::begin(cudaStream_t s, const char* name, double bytes) {
+  int idx = -1;
+  for (size_t i = 0; i < table_.size(); ++i)
+    if (table_[i].name == name || std::strcmp(table_[i].name, name) == 0) { idx = (int)i; break; }
+  if (idx < 0) {
+    table_.push_back(KernelProfile{name, 0ULL, 0.0, 0.0});
+    idx = (int)table_.size() - 1;
+  }
+  table_[idx].launches++;
+  table_[idx].bytes += bytes;
+  cur_idx_ = idx;
+  cur0_ = get_event();
+  AB200_CUDA_CHECK(cudaEventRecord(cur0_, s));
+}
+void Profiler::end(cudaStream_t s) {
+  cudaEvent_t e1 = get_event();
+  AB200_CUDA_CHECK(cudaEventRecord(e1, s));
+  pending_.push_back(Pending{cur_idx_, cur0_, e1});
+  if (pending_.size() >= 8192) flush();
+}
+void Profiler::flush() {
+  for (auto& p : pending_) {
+    float ms = 0.f;
+    cudaEventSynchronize(p.e1);
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) table_[p.idx].ms += ms;
+    pool_.push_back(p.e0);
+    pool_.push_back(p.e1);
+  }
+  pending_.clear();
+}
+void Profiler::reset() {
+  flush();
+  table_.clear();
+}
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -552,6 +601,7 @@ template <typename T>
 void CudaVecOps<T>::axpby_norm(int64_t n, T a, T b, const T* x, T* y, T* out) {
   const int grid = reduce_grid(n);
   ensure_partial((size_t)grid);
+  ProfScope ps(stream_, "axpby_norm", (double)sizeof(T) * n * (x ? 3.0 : 2.0));
   k_axpby_norm<T><<<grid, kThreads, 0, stream_>>>(n, a, b, x, y, partial_, out, ticket_);
   AB200_LAUNCHED();
 }
@@ -559,6 +609,7 @@ template <typename T>
 void CudaVecOps<T>::dot(int64_t n, const T* x, const T* y, T* out) {
   const int grid = reduce_grid(n);
   ensure_partial((size_t)grid);
+  ProfScope ps(stream_, "dot", (double)sizeof(T) * n * (x == y ? 1.0 : 2.0));
   k_dot<T><<<grid, kThreads, 0, stream_>>>(n, x, y, partial_, out, ticket_);
   AB200_LAUNCHED();
 }
@@ -590,6 +641,7 @@ void CudaVecOps<T>::larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) {
 template <typename T>
 void CudaVecOps<T>::start_step(int64_t n, T inv, const T* resid, T* vj, T* outx, T* bx, bool from_resid) {
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
+  ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? (from_resid ? 4.0 : 5.0) : 3.0));
   k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid);
   AB200_LAUNCHED();
 }
@@ -614,6 +666,7 @@ void CudaVecOps<T>::dots_generic(int64_t n, int j, const T* v, int64_t ldv, cons
   const int grid = reduce_grid(n);
   const int pcols = j + 1;
   ensure_partial((size_t)grid * pcols);
+  ProfScope ps(stream_, "dots_generic", (double)sizeof(T) * n * (j + (x == y ? 1.0 : 2.0)));
   k_dots<T, CC><<<grid, kThreads, 0, stream_>>>(n, j, v, ldv, x, y, partial_, pcols, out, ticket_);
   AB200_LAUNCHED();
   launch_stats().fallback++;
@@ -623,6 +676,7 @@ void CudaVecOps<T>::update_generic(int64_t n, int j, const T* v, int64_t ldv, co
                                    T* dst, T* nrm2, const T* pw2, const T* pr2, T* flag) {
   const int grid = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)num_sms_ * 8);
   ensure_partial((size_t)grid);
+  ProfScope ps(stream_, pw2 ? "reorth_generic" : "update_generic", (double)sizeof(T) * n * (j + 2.0));
   k_update<T><<<grid, kThreads, sizeof(T) * (size_t)std::max(j, 1), stream_>>>(n, j, v, ldv, coef, src, dst,
                                                                                partial_, nrm2, ticket_, pw2, pr2,
                                                                                flag);
@@ -657,6 +711,13 @@ void CudaVecOps<T>::orth_step(int64_t n, int j, const T* v, int64_t ldv, const T
 }
 
 template <typename T>
+void CudaVecOps<T>::vq_smem_attr(int kin) {
+  const size_t bytes = sizeof(T) * 33 * (size_t)kin;
+  if (bytes > 48 * 1024)
+    AB200_CUDA_CHECK(cudaFuncSetAttribute(k_vq<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+template <typename T>
 void CudaVecOps<T>::vq_update(int64_t n, int kin, int kout, T* v, int64_t ldv, const T* q_host, int ldq,
                               bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2) {
   if (kout <= 0) {
@@ -669,6 +730,8 @@ void CudaVecOps<T>::vq_update(int64_t n, int kin, int kout, T* v, int64_t ldv, c
     return;
   const int grid = (int)std::min<int64_t>((n + 31) / 32, (int64_t)num_sms_ * 6);
   ensure_partial((size_t)grid);
+  ProfScope ps(stream_, "vq_generic", (double)sizeof(T) * n * (kin + kout + (with_resid ? 2.0 : 0.0)));
+  vq_smem_attr(kin);
   k_vq<T><<<grid, kThreads, sizeof(T) * 33 * (size_t)kin, stream_>>>(n, kin, kout, v, ldv, qdev, v, ldv,
                                                                       with_resid, sigma, beta, beta_col, resid,
                                                                       partial_, mb_nrm2, ticket_);
@@ -685,6 +748,8 @@ void CudaVecOps<T>::vq_out(int64_t n, int kin, int kout, const T* v, int64_t ldv
     return;
   const int grid = (int)std::min<int64_t>((n + 31) / 32, (int64_t)num_sms_ * 6);
   ensure_partial((size_t)grid);
+  ProfScope ps(stream_, "vq_generic", (double)sizeof(T) * n * (kin + kout));
+  vq_smem_attr(kin);
   k_vq<T><<<grid, kThreads, sizeof(T) * 33 * (size_t)kin, stream_>>>(n, kin, kout, v, ldv, qdev, out, ldo, false,
                                                                       T(0), T(0), -1, nullptr, partial_, nullptr,
                                                                       ticket_);

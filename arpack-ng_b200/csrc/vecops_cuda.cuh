@@ -38,6 +38,45 @@ struct LaunchStats {
 };
 LaunchStats& launch_stats();
 
+// Per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).  Disabled by
+// default; when enabled every profiled launch is bracketed by two event records and the elapsed times
+// are accumulated per kernel name together with the algorithmic bytes the launch was charged with.
+struct KernelProfile {
+  const char* name;
+  unsigned long long launches;
+  double ms;
+  double bytes;
+};
+class Profiler {
+ public:
+  bool enabled = false;
+  void begin(cudaStream_t s, const char* name, double bytes);
+  void end(cudaStream_t s);
+  void flush();  // synchronises the pending events and accumulates
+  void reset();
+  const std::vector<KernelProfile>& table() { flush(); return table_; }
+
+ private:
+  struct Pending { int idx; cudaEvent_t e0, e1; };
+  std::vector<KernelProfile> table_;
+  std::vector<Pending> pending_;
+  std::vector<cudaEvent_t> pool_;
+  cudaEvent_t cur0_ = nullptr;
+  int cur_idx_ = -1;
+  cudaEvent_t get_event();
+};
+Profiler& profiler();
+struct ProfScope {
+  cudaStream_t s;
+  bool on;
+  ProfScope(cudaStream_t stream, const char* name, double bytes) : s(stream), on(profiler().enabled) {
+    if (on) profiler().begin(s, name, bytes);
+  }
+  ~ProfScope() {
+    if (on) profiler().end(s);
+  }
+};
+
 template <typename T>
 class CudaVecOps final : public VecOps<T> {
  public:
@@ -111,6 +150,7 @@ class CudaVecOps final : public VecOps<T> {
   T* stage_matrix(const T* host, int rows, int cols, int ld);  // -> device, packed rows x cols, column-major
   bool fast_path_ok(int64_t n, int j, const T* v, int64_t ldv) const;
   int reduce_grid(int64_t n) const;
+  void vq_smem_attr(int kin);
 
   // generic kernels (vecops_cuda.cu)
   void dots_generic(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out);

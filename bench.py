@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- Lanczos steps/s of the dsaupd hot path on BASELINE.json's config 2.
+
+  python bench.py --gpus N --steps K --warmup W          our arm (CUDA, one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                   the reference algorithm on the host cores (oracle port)
+
+One bench "step" = one dsaupd_c run with a fixed restart budget (--restarts R: nev + R*(ncv - kev) Lanczos steps,
+exits with info = 1) on the 2-D 5-point Laplacian nx x nx (n = nx^2, CSR FP64), nev=10, ncv=40, which='LA',
+tol=1e-10, start vector = the hashed vector of SURVEY.md §8(d).  value = OP*x count (iparam(9)) / time.
+
+  value : device-resident path -- A, resid, V, workd live in HBM, the ido=+-1 hand-off passes device pointers to
+          the CSR SpMV kernel; timed with CUDA events on the library's stream, max over ranks.
+  e2e   : the same solve through dsaupd_c with HOST (pinned) resid/V/workd exactly as an unmodified caller of the
+          reference owns them; every hand-off crosses PCIe (library: D2H x, H2D y; OP: H2D x, SpMV, D2H y) and V/resid
+          come back at ido=99.  Byte counts are summed from the copies actually issued.
+  roofline : the dominant kernel of the timed region (by accumulated CUDA-event time), achieved = algorithmic bytes
+          charged per launch / event time, against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline : the oracle port (oracle/libref_arpack.so + OpenBLAS, all host threads) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NEV, NCV, WHICH, TOL = 10, 40, "LA", 1e-10
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_solve_sample(nx, restarts, threads, steps=1, warmup=0):
+    """dsaupd (oracle restatement of SRC/dsaupd.f..dsapps.f) + threaded CSR SpMV on nx x nx, fixed restart budget."""
+    from backends import lib as oracle_lib
+    import arpack_ng_b200 as ab
+    L = oracle_lib()
+    n = nx * nx
+    nnz = 5 * n - 4 * nx
+    rowptr = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(nnz, dtype=np.int32)
+    val = np.empty(nnz, dtype=np.float64)
+    ip, dp = (lambda a: a.ctypes.data_as(C.POINTER(C.c_int))), (lambda a: a.ctypes.data_as(C.POINTER(C.c_double)))
+    assert L.ref_gen_laplace2d(nx, nx, 1.0, ip(rowptr), ip(col), dp(val)) == nnz
+    L.ref_set_blas_threads(threads)
+    r0 = ab.hashed_start_vector_numpy(n)
+    v = np.zeros(n * NCV)
+    counts = np.zeros(5, dtype=np.int32)
+    times = []
+    nopx = 0
+    for it in range(warmup + steps):
+        ctx = C.c_void_p(L.ref_ctx_new())
+        resid = r0.copy()
+        tt, top = C.c_double(), C.c_double()
+        info = L.ref_dsaupd_csr_solve(ctx, n, ip(rowptr), ip(col), dp(val), WHICH.encode(), NEV, NCV, TOL, restarts, 1,
+                                      dp(resid), dp(v), None, None, None, ip(counts), threads, C.byref(tt),
+                                      C.byref(top))
+        L.ref_ctx_free(ctx)
+        if it >= warmup:
+            times.append(tt.value)
+            nopx = int(counts[2])
+    return {"seconds": times, "nopx": nopx, "info": int(info), "restarts": int(counts[0]), "nrorth": int(counts[4])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    restarts = 1  # bounded sample: nev + one restart sweep = 40 OP*x on the full-size operator
+    r = cpu_solve_sample(args.nx, restarts, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    total = sum(r["seconds"])
+    value = r["nopx"] * len(r["seconds"]) / total
+    sample = (f"same operator (2-D Laplacian {args.nx}x{args.nx}, CSR FP64) and solver parameters, restart budget "
+              f"mxiter={restarts} ({r['nopx']} OP*x per step) instead of {args.restarts}")
+    out = {"impl": "reference", "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(r["seconds"]),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, restarts),
+           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference = arpack-ng's dsaupd algorithm restated in C (oracle/) on OpenBLAS, all host threads; the "
+                   "Fortran reference itself cannot be compiled in this image (no Fortran compiler)"}
+    print(json.dumps(out))
+
+
+def workload_config(args, restarts):
+    return {"workload": f"BASELINE config 2: dsaupd on 2-D 5-point Laplacian {args.nx}x{args.nx} (n={args.nx * args.nx}) "
+                        f"CSR FP64, nev={NEV} ncv={NCV} which={WHICH} tol={TOL}, fixed restart budget",
+            "nx": args.nx, "n": args.nx * args.nx, "nev": NEV, "ncv": NCV, "which": WHICH, "tol": TOL,
+            "restarts_per_step": restarts, "start_vector": "splitmix64 hash, info=1",
+            "l2": "inputs larger than L2 (V alone is %.1f GB)" % (args.nx * args.nx * NCV * 8 / 1e9)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import arpack_ng_b200 as ab
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = ab.nccl_comm_from_torch_distributed()
+    L = ab.lib()
+    nx = args.nx
+    n_global = nx * nx
+    # row (y-slab) partition, PARPACK's block-row layout (dsaupd.f:331-349)
+    base, rem = divmod(nx, world)
+    nyloc = base + (1 if rank < rem else 0)
+    y0 = rank * base + min(rank, rem)
+    if world == 1:
+        A = ab.CsrOperator.laplace2d(nx, nx)
+        op = A
+    else:
+        A = ab.CsrOperator.laplace3d(nx, 1, nx, z0=y0, nzloc=nyloc, diag=4.0)
+
+        def op(x, y, *_):
+            A.apply_halo(comm, x, y)
+    n = A.n
+    r0 = ab.hashed_start_vector(n, i0=y0 * nx)
+    restarts = args.restarts
+
+    def one_solve(host_buffers=False, resid=None):
+        return ab.solve(op, n, NEV, NCV, WHICH, tol=TOL, mxiter=restarts, resid=resid if resid is not None else r0,
+                        eupd=False, host_buffers=host_buffers, comm=comm)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = one_solve()
+    barrier()
+    ab.profile(enable=True, reset=True)
+    st0 = ab.launch_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    nopx = 0
+    for _ in range(args.steps):
+        res = one_solve()
+        nopx += int(res.iparam[8])
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = ev0.elapsed_time(ev1) / 1e3
+    prof = ab.profile(enable=False)
+    st1 = ab.launch_stats()
+    if dist is not None:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = nopx / elapsed
+
+    # ---- e2e: host buffers through the reference-facing C-ABI (N = 1 only: one PCIe link per GPU anyway) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        r0h = r0.cpu().numpy()
+        e2e_steps = max(1, min(args.steps, 2))
+        one_solve(host_buffers=True, resid=r0h)  # warm-up (pinned allocation, page faults)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nop2 = 0
+        for _ in range(e2e_steps):
+            rr = one_solve(host_buffers=True, resid=r0h)
+            nop2 += int(rr.iparam[8])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        per = nop2 // e2e_steps
+        w = 8
+        # library: H2D resid once; per hand-off D2H x + H2D y; at ido=99 D2H V + resid.  OP: H2D x + D2H y per call
+        h2d = n * w + per * (n * w) + per * (n * w)
+        d2h = per * (n * w) + per * (n * w) + n * NCV * w + n * w
+        e2e = {"value": nop2 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "bench_steps": e2e_steps, "buffers": "pinned host resid/V/workd, OP = H2D + CSR SpMV kernel + D2H"}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    # dominant kernel by accumulated event time
+    roof = None
+    if prof:
+        name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        total_ms = sum(v["ms"] for v in prof.values())
+        ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(name, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        step_bytes = sum(v["bytes"] for v in prof.values())
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "launches": top["launches"],
+                "avg_launch_ms": top["ms"] / max(1, top["launches"]), "share_of_kernel_time": top["ms"] / total_ms,
+                "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
+                "all_kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                                    "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "lanczos_step_aggregate": {"algorithmic_GB_per_s": step_bytes / elapsed / 1e9,
+                                           "frac_of_peak": step_bytes / elapsed / 1e9 / (peak * world),
+                                           "kernel_time_share_of_elapsed": total_ms * 1e-3 / elapsed}}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        c = cpu_solve_sample(nx, 1, threads)
+        cv = c["nopx"] / c["seconds"][0]
+        cpu = {"value": cv, "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"same operator and parameters with restart budget mxiter=1 ({c['nopx']} OP*x, "
+                         f"{c['seconds'][0]:.1f} s), oracle port + OpenBLAS, {threads} threads"}
+    out = {"metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, restarts), "lanczos_steps_per_bench_step": nopx // args.steps,
+           "ms_per_lanczos_step": 1e3 * elapsed / nopx, "info": int(res.info), "wall_s": wall,
+           "gpu_launches": st1["kernels"] - st0["kernels"], "allreduces": st1["allreduces"] - st0["allreduces"],
+           "kernel_path": {"tma": st1["tma_path"] - st0["tma_path"], "generic": st1["generic_path"] - st0["generic_path"]},
+           "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--restarts", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

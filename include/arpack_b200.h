@@ -133,6 +133,10 @@ void ab200_release_all(void);
 void ab200_launch_stats(unsigned long long* out4);
 /* forget the SAVE'd dgetv0 seed / dnaitr smlnum, as if the process had just started */
 void ab200_reset_seed(void);
+/* per-kernel CUDA-event timing on the launching stream (bench.py's roofline): enable, run, read the table */
+void ab200_profile_enable(int on);
+void ab200_profile_reset(void);
+int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* launches, double* bytes);
 int ab200_device_count(void);
 const char* ab200_version(void);
 
@@ -158,7 +162,10 @@ int ab200_csr_spmv_halo_f64(int comm, int nloc, int halo_lo, int halo_hi, const 
 /* synthetic operators of BASELINE.json's configs, generated on the device; each returns nnz (or < 0).
  * Call with rowptr = NULL to query nnz only. */
 long long ab200_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val);
-long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, int* rowptr, int* col, double* val);
+/* 7-point stencil (diag, -1) on nx x ny x nz, z-slab [z0, z0+nzloc) with halo columns; ny = 1, diag = 4 gives the
+ * y-slab of the 2-D 5-point Laplacian */
+long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, double diag, int* rowptr, int* col,
+                              double* val);
 long long ab200_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double* val);
 /* start vector of SURVEY.md §8(d): resid[i] = 2 u(i0+i) - 1, u = top 53 bits of splitmix64(seed + i) / 2^53 */
 int ab200_fill_hash_f64(long long n, long long i0, unsigned long long seed, double* x);

@@ -88,6 +88,9 @@ void ref_dlarnv2(int* iseed4, int n, double* x);
 void ref_csr_spmv(int nrows, const int* rowptr, const int* col, const double* val, const double* x,
                   double* y, int nthreads);
 
+/* 2-D 5-point Laplacian (4,-1)*scale in CSR built on the CPU (operator of BASELINE config 2); returns nnz */
+long long ref_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val);
+
 /* Run a whole symmetric solve (dsaupd loop + optional dseupd) on a CSR operator, mode 1, bmat='I'.
  * Used for timing the CPU baseline without Python in the loop.  Returns info of dsaupd.
  * out_counts = {iparam(3), iparam(5), nopx, nbx, nrorth}; d (nev) and z (n*nev, may be NULL). */

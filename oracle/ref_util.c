@@ -50,6 +50,26 @@ void ref_csr_spmv(int nrows, const int* rowptr, const int* col, const double* va
   }
 }
 
+/* 2-D 5-point Laplacian (4, -1)*scale in CSR, row-major natural ordering (BASELINE config 2 operator),
+ * built on the CPU for the reference arm of bench.py.  Returns nnz; arrays sized by the caller
+ * (nnz = 5*nx*ny - 2*nx - 2*ny). */
+long long ref_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val) {
+  long long p = 0;
+  for (int iy = 0; iy < ny; ++iy) {
+    for (int ix = 0; ix < nx; ++ix) {
+      const long long r = (long long)iy * nx + ix;
+      rowptr[r] = (int)p;
+      if (iy > 0) { col[p] = (int)(r - nx); val[p] = -scale; ++p; }
+      if (ix > 0) { col[p] = (int)(r - 1); val[p] = -scale; ++p; }
+      col[p] = (int)r; val[p] = 4.0 * scale; ++p;
+      if (ix < nx - 1) { col[p] = (int)(r + 1); val[p] = -scale; ++p; }
+      if (iy < ny - 1) { col[p] = (int)(r + nx); val[p] = -scale; ++p; }
+    }
+  }
+  rowptr[(long long)nx * ny] = (int)p;
+  return p;
+}
+
 static double now_s(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -58,6 +58,8 @@ def lib():
                                            C.c_int, C.c_double, C.c_int, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
                                            c_dbl_p, c_int_p, C.c_int, c_dbl_p, c_dbl_p]
         L.ref_dsaupd_csr_solve.restype = C.c_int
+        L.ref_gen_laplace2d.argtypes = [C.c_int, C.c_int, C.c_double, c_int_p, c_int_p, c_dbl_p]
+        L.ref_gen_laplace2d.restype = C.c_longlong
         _lib = L
     return _lib
 
