@@ -506,6 +506,9 @@ T* CudaVecOps<T>::mailbox(size_t count) {
     mb_count_ = count;
   }
   AB200_CUDA_CHECK(cudaMemsetAsync(mb_dev_, 0, sizeof(T) * mb_count_, stream_));
+  // size the reduction scratch once for the whole solve (largest grid x one mailbox segment), so that
+  // no step ever pays a synchronising cudaFree/cudaMalloc
+  ensure_partial((size_t)num_sms_ * 8 * (count / 3 + 2));
   return mb_dev_;
 }
 template <typename T>
