@@ -503,6 +503,39 @@ int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* lau
   }
   return (int)t.size();
 }
+// Kernel micro-benchmark hook (tools/kernel_sweep.py): run `iters` orthogonalisation steps (what = 0), multi-dots
+// (1) or restart updates V <- V*Q with kout columns (2) on synthetic data of the given shape.  Timings are read back
+// through the profiler table.  Returns 0 on success.
+int ab200_kernel_probe_f64(long long n, int j, int ncv, int iters, int what, int kout) {
+  try {
+    require_device();
+    CudaVecOps<double> ops(g_stream, nullptr);
+    ops.set_kernel_mode(g_kernel_mode);
+    const int64_t ldv = (n + 1) & ~1LL;
+    double* v = ops.alloc((size_t)ldv * ncv);
+    double* w = ops.alloc((size_t)n);
+    double* r = ops.alloc((size_t)n);
+    double* mb = ops.mailbox((size_t)3 * (ncv + 2));
+    ab200_fill_hash_f64(ldv * (long long)ncv, 0, 1234567ULL, v);
+    ab200_fill_hash_f64(n, 0, 7654321ULL, w);
+    ops.scal((int64_t)ldv * ncv, 1e-3, v);
+    std::vector<double> q((size_t)ncv * ncv, 0.0);
+    for (int c = 0; c < ncv; ++c)
+      for (int k = 0; k < ncv; ++k) q[(size_t)c * ncv + k] = (k == c) ? 1.0 : 1e-3 / (1 + k + c);
+    ops.sync();
+    for (int it = 0; it < iters; ++it) {
+      if (what == 0) ops.orth_step(n, j, v, ldv, w, r, mb, mb + ncv + 2, mb + 2 * (ncv + 2));
+      else if (what == 1) ops.dots(n, j, v, ldv, w, w, mb);
+      else ops.vq_update(n, ncv, kout, v, ldv, q.data(), ncv, true, 0.5, 0.25, kout - 1, r, mb);
+    }
+    ops.sync();
+    ops.release(v); ops.release(w); ops.release(r);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: kernel_probe: %s\n", e.what());
+    return -1;
+  }
+}
 int ab200_device_count(void) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/arpack_b200.h"
@@ -50,6 +51,57 @@ __global__ void __launch_bounds__(256) k_csr_spmv(int nrows, const int* __restri
   }
 }
 
+// "CSR-stream" variant for short rows: a CTA owns ROWS consecutive rows, multiplies their non-zeros
+// in the coalesced order of the val/col streams (thread i takes entries i, i+ROWS, ...; four
+// independent col/val loads and four x gathers in flight per thread), parks the products in shared
+// memory, then every thread sums its own row in order.  Only two dependent memory levels per entry
+// instead of the three of the row-per-sub-warp kernel, and deterministic row sums.
+template <typename T, int ROWS, int CAP>
+__global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* __restrict__ rowptr,
+                                                          const int* __restrict__ col, const T* __restrict__ val,
+                                                          const T* __restrict__ x, T* __restrict__ y, int nloc,
+                                                          const T* __restrict__ xh) {
+  __shared__ T prod[CAP];
+  __shared__ int srow[ROWS + 1];
+  const int tid = threadIdx.x;
+  for (long long blk = blockIdx.x; blk * ROWS < nrows; blk += gridDim.x) {
+    const int r0 = (int)(blk * ROWS);
+    const int nr = (nrows - r0 < ROWS) ? (nrows - r0) : ROWS;
+    if (tid < nr) srow[tid] = rowptr[r0 + tid];
+    if (tid == 0) srow[nr] = rowptr[r0 + nr];
+    __syncthreads();
+    const int p0 = srow[0], p1 = srow[nr];
+    const int rs = (tid < nr) ? srow[tid] : p1, re = (tid < nr) ? srow[tid + 1] : p1;
+    T acc = T(0);
+    for (int c0 = p0; c0 < p1; c0 += CAP) {
+      const int c1 = (c0 + CAP < p1) ? c0 + CAP : p1;
+      int i = c0 + tid;
+      for (; i + 3 * ROWS < c1; i += 4 * ROWS) {
+        const int ca = col[i], cb = col[i + ROWS], cc = col[i + 2 * ROWS], cd = col[i + 3 * ROWS];
+        const T va = val[i], vb = val[i + ROWS], vc = val[i + 2 * ROWS], vd = val[i + 3 * ROWS];
+        const T xa = (xh != nullptr && ca >= nloc) ? xh[ca - nloc] : x[ca];
+        const T xb = (xh != nullptr && cb >= nloc) ? xh[cb - nloc] : x[cb];
+        const T xc = (xh != nullptr && cc >= nloc) ? xh[cc - nloc] : x[cc];
+        const T xd = (xh != nullptr && cd >= nloc) ? xh[cd - nloc] : x[cd];
+        prod[i - c0] = va * xa;
+        prod[i + ROWS - c0] = vb * xb;
+        prod[i + 2 * ROWS - c0] = vc * xc;
+        prod[i + 3 * ROWS - c0] = vd * xd;
+      }
+      for (; i < c1; i += ROWS) {
+        const int ca = col[i];
+        const T xa = (xh != nullptr && ca >= nloc) ? xh[ca - nloc] : x[ca];
+        prod[i - c0] = val[i] * xa;
+      }
+      __syncthreads();
+      const int a = (rs > c0) ? rs : c0, b = (re < c1) ? re : c1;
+      for (int q = a; q < b; ++q) acc += prod[q - c0];
+      __syncthreads();
+    }
+    if (tid < nr) y[r0 + tid] = acc;
+  }
+}
+
 template <typename T>
 int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, const T* x, T* y, int nloc,
                 const T* xh, long long nnz_hint) {
@@ -59,6 +111,16 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   cudaStream_t s = cur_stream();
   const long long nnz = nnz_hint > 0 ? nnz_hint : 0;
   ProfScope ps(s, "csr_spmv", (double)nnz * (sizeof(T) + 4.0) + (nrows + 1) * 4.0 + 2.0 * nrows * sizeof(T));
+  static const bool use_stream = (getenv("AB200_SPMV") == nullptr || std::strcmp(getenv("AB200_SPMV"), "subwarp") != 0);
+  if (use_stream && avg <= 8.5) {
+    constexpr int ROWS = 256, CAP = 2304;
+    long long g = ((long long)nrows + ROWS - 1) / ROWS;
+    const long long cap = 148LL * 8;
+    const int grid = (int)(g > cap ? cap : g);
+    k_csr_spmv_stream<T, ROWS, CAP><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
+    launch_stats().kernels++;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   auto grid_for = [&](int lpr) {
     long long g = ((long long)nrows * lpr + threads - 1) / threads;
     const long long cap = 148LL * 32;

@@ -28,7 +28,8 @@ constexpr int CB = 8;             // columns per TMA box == number of consumer w
 constexpr int NCW = 8;            // consumer warps
 constexpr int MAXB = 8;           // column boxes per tile -> j <= 64
 constexpr int MAXST = 12;         // ring depth limit
-constexpr int kThreadsTma = (NCW + 1) * 32;
+constexpr int NG = 2;              // consumer groups (alternate tiles)
+constexpr int kThreadsTma = (NG * NCW + 1) * 32;
 constexpr uint32_t kTileBudget = 192 * 1024;
 
 enum Mode { DOTS = 0, UPD = 1, UPD_SPEC = 2 };
@@ -134,9 +135,10 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
   }
   T* tiles = reinterpret_cast<T*>(smem);
   unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
-  T* ps = reinterpret_cast<T*>(aux);                     // [2 buffers][2 halves][R]
-  T* cs = ps + 4 * R;                                    // [MAXB*CB] coefficients
-  uint64_t* full = reinterpret_cast<uint64_t*>(cs + MAXB * CB);
+  T* ps = reinterpret_cast<T*>(aux);                     // [NG groups][2 buffers][2 halves][R]
+  T* cs = ps + NG * 4 * R;                               // [MAXB*CB] coefficients
+  T* gsum = cs + MAXB * CB;                              // [MAXB*CB + 8] partials of consumer group 1
+  uint64_t* full = reinterpret_cast<uint64_t*>(gsum + MAXB * CB + 8);
   uint64_t* empty = full + MAXST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
   const int64_t ntiles = (p.n + R - 1) / R;
   const uint32_t stage_elems = p.stage_bytes / sizeof(T);
 
-  if (warp == NCW) {
+  if (warp == NG * NCW) {
     // ---------------- producer: one elected lane feeds the ring ----------------
     if (lane == 0) {
       int it = 0;
@@ -167,24 +169,35 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
       }
     }
   } else {
-    // ---------------- consumers ----------------
+    // ---------------- consumers: NG groups of NCW warps take alternate tiles, so that one group's
+    // latency-bound phases overlap the other's ----------------
+    const int g = warp / NCW, gw = warp - g * NCW, gtid = tid - g * NCW * 32;
     T acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = T(0);
     T accn = T(0);
     const bool y_is_x = (p.y == p.x);
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    // the vector operand (4 rows per lane) is software-prefetched one tile ahead: its global-load
+    // latency would otherwise sit on the critical path of every tile
+    T xn[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int64_t r = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * R + lane + 32 * m;
+      xn[m] = (r < p.n) ? p.x[r] : T(0);
+    }
+    int it = g;
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
       const int s = it % p.nstages;
       const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
       const int64_t row0 = t * R;
       T xv[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int64_t r = row0 + lane + 32 * m;
-        xv[m] = (r < p.n) ? p.x[r] : T(0);
+        xv[m] = xn[m];
+        const int64_t r = row0 + (int64_t)NG * gridDim.x * R + lane + 32 * m;
+        xn[m] = (r < p.n) ? p.x[r] : T(0);
       }
-      if (MODE == DOTS && warp == 0) {
+      if (MODE == DOTS && gw == 0) {
         if (y_is_x) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) accn += xv[m] * xv[m];
@@ -200,29 +213,31 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
       const T* tile = tiles + (size_t)s * stage_elems;
       if (MODE != DOTS) {
         // phase 1: row-local product V(i,:)*coef, columns split in two interleaved halves
-        const int row = tid & (R - 1), half = tid >> 7;
+        const int row = gtid & (R - 1), half = gtid >> 7;
         const T* tr = tile + row;
         T a0 = T(0), a1 = T(0);
         int c = half;
+#pragma unroll 4
         for (; c + 2 < p.j; c += 4) {
           a0 += tr[c * R] * cs[c];
           a1 += tr[(c + 2) * R] * cs[c + 2];
         }
         if (c < p.j) a0 += tr[c * R] * cs[c];
-        T* psb = ps + (it & 1) * 2 * R;
+        T* psb = ps + g * 4 * R + ((it / NG) & 1) * 2 * R;
         psb[half * R + row] = a0 + a1;
-        consumer_bar_sync();
+        if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(NCW * 32) : "memory");
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const int rr = lane + 32 * m;
           xv[m] = xv[m] - (psb[rr] + psb[R + rr]);
         }
-        if (warp < 4) {
-          const T rq = (warp == 0) ? xv[0] : (warp == 1) ? xv[1] : (warp == 2) ? xv[2] : xv[3];
-          const int64_t r = row0 + lane + 32 * warp;
+        if (gw < 4) {
+          const T rq = (gw == 0) ? xv[0] : (gw == 1) ? xv[1] : (gw == 2) ? xv[2] : xv[3];
+          const int64_t r = row0 + lane + 32 * gw;
           if (r < p.n) p.dst[r] = rq;
         }
-        if (warp == 0) {
+        if (gw == 0) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) accn += xv[m] * xv[m];
         }
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
           if (b < p.nboxes) {
-            const T* col = tile + (size_t)(b * CB + warp) * R + lane;
+            const T* col = tile + (size_t)(b * CB + gw) * R + lane;
             acc[b] += (col[0] * xv[0] + col[32] * xv[1]) + (col[64] * xv[2] + col[96] * xv[3]);
           }
         }
@@ -240,21 +255,30 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
-    // per-CTA partials
+    // per-CTA partials: group 1 parks its warp sums in shared memory, group 0 adds its own and publishes
     T* mine = p.partial + (size_t)blockIdx.x * p.pcols;
     if (MODE != UPD) {
 #pragma unroll
-      for (int b = 0; b < MAXB; ++b) {
-        if (b < p.nboxes) {
-          const T v = warp_sum(acc[b]);
-          const int c = b * CB + warp;
-          if (lane == 0 && c < p.j) mine[c] = v;
+      for (int b = 0; b < MAXB; ++b) acc[b] = warp_sum(acc[b]);
+    }
+    accn = warp_sum(accn);
+    if (g == 1 && lane == 0) {
+      if (MODE != UPD) {
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) gsum[b * CB + gw] = acc[b];
+      }
+      if (gw == 0) gsum[MAXB * CB] = accn;
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(NG * NCW * 32) : "memory");
+    if (g == 0 && lane == 0) {
+      if (MODE != UPD) {
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+          const int c = b * CB + gw;
+          if (b < p.nboxes && c < p.j) mine[c] = acc[b] + gsum[c];
         }
       }
-    }
-    if (warp == 0 && p.out != nullptr) {
-      const T v = warp_sum(accn);
-      if (lane == 0) mine[(MODE == UPD) ? 0 : p.j] = v;
+      if (gw == 0 && p.out != nullptr) mine[(MODE == UPD) ? 0 : p.j] = accn + gsum[MAXB * CB];
     }
   }
   if (p.out == nullptr) return;
@@ -329,7 +353,7 @@ bool make_tmap_uncached(CUtensorMap* map, const T* v, int64_t n, int64_t ldv, in
 
 template <typename T>
 size_t aux_bytes() {
-  return sizeof(T) * (4 * R + MAXB * CB) + sizeof(uint64_t) * 2 * MAXST;
+  return sizeof(T) * (NG * 4 * R + 2 * MAXB * CB + 8) + sizeof(uint64_t) * 2 * MAXST;
 }
 
 template <typename T>

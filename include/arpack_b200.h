@@ -137,6 +137,8 @@ void ab200_reset_seed(void);
 void ab200_profile_enable(int on);
 void ab200_profile_reset(void);
 int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* launches, double* bytes);
+/* kernel micro-benchmark on synthetic data (tools/kernel_sweep.py): what = 0 orth step, 1 multi-dots, 2 V*Q update */
+int ab200_kernel_probe_f64(long long n, int j, int ncv, int iters, int what, int kout);
 int ab200_device_count(void);
 const char* ab200_version(void);
 
