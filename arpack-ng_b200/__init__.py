@@ -88,6 +88,9 @@ def lib():
     L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.ab200_device_count.restype = C.c_int
     L.ab200_kernel_probe_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ab200_debug_orth_f64.argtypes = [C.c_longlong, C.c_int, vp, C.c_longlong, vp, vp, vp]
+    L.ab200_debug_vq_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_double, C.c_double,
+                                     C.c_int, vp, vp]
     L.ab200_profile_enable.argtypes = [C.c_int]
     L.ab200_profile_get.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
                                     C.POINTER(C.c_double)]

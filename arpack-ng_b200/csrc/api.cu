@@ -503,6 +503,50 @@ int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* lau
   }
   return (int)t.size();
 }
+// Kernel unit-test hooks (tests/test_gpu_kernels.py): run ONE fused orthogonalisation step / restart update on
+// caller-supplied DEVICE arrays and hand the mailbox back, so that each kernel can be compared with a plain
+// reference of the same op independently of the solver.
+//   out_host[0..j]      = h = V_j^T w, ||w||^2
+//   out_host[j+1..2j+1] = s = V_j^T r, ||r||^2     (r = w - V_j h, written to resid)
+//   out_host[2j+2]      = ||r'||^2 (r' = r - V_j s), out_host[2j+3] = 1 if the DGKS pass ran (then resid = r')
+int ab200_debug_orth_f64(long long n, int j, const double* v, long long ldv, const double* w, double* resid,
+                         double* out_host) {
+  try {
+    require_device();
+    CudaVecOps<double> ops(g_stream, nullptr);
+    ops.set_kernel_mode(g_kernel_mode);
+    const int seg = j + 2;
+    double* mb = ops.mailbox((size_t)3 * seg);
+    ops.orth_step(n, j, v, ldv, w, resid, mb, mb + seg, mb + 2 * seg);
+    std::vector<double> h((size_t)3 * seg);
+    ops.fetch(h.data(), mb, (size_t)3 * seg);
+    for (int i = 0; i <= j; ++i) out_host[i] = h[i];
+    for (int i = 0; i <= j; ++i) out_host[j + 1 + i] = h[seg + i];
+    out_host[2 * j + 2] = h[2 * seg];
+    out_host[2 * j + 3] = h[2 * seg + 1];
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: debug_orth: %s\n", e.what());
+    return -1;
+  }
+}
+// V(:,0:kout) <- V(:,0:kin)*Q (q_host column-major kin x kout), resid <- sigma*resid + beta*Vnew(:,beta_col);
+// *nrm2_host = ||resid||^2
+int ab200_debug_vq_f64(long long n, int kin, int kout, double* v, long long ldv, const double* q_host, double sigma,
+                       double beta, int beta_col, double* resid, double* nrm2_host) {
+  try {
+    require_device();
+    CudaVecOps<double> ops(g_stream, nullptr);
+    ops.set_kernel_mode(g_kernel_mode);
+    double* mb = ops.mailbox(8);
+    ops.vq_update(n, kin, kout, v, ldv, q_host, kin, true, sigma, beta, beta_col, resid, mb);
+    ops.fetch(nrm2_host, mb, 1);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: debug_vq: %s\n", e.what());
+    return -1;
+  }
+}
 // Kernel micro-benchmark hook (tools/kernel_sweep.py): run `iters` orthogonalisation steps (what = 0), multi-dots
 // (1) or restart updates V <- V*Q with kout columns (2) on synthetic data of the given shape.  Timings are read back
 // through the profiler table.  Returns 0 on success.

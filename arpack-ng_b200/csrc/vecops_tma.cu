@@ -1,36 +1,41 @@
 // vecops_tma.cu -- TMA-tiled fast path of the tall-skinny kernels (sm_100a).
 //
 // One persistent CTA per SM streams V(n x j) through shared memory in tiles of R = 128 rows x all
-// j columns.  A producer warp issues one 2-D TMA box copy (cp.async.bulk.tensor) per 8 columns into a
-// ring of mbarrier-guarded stages; eight consumer warps work on the tile from shared memory:
+// j columns.  A producer warp issues one 2-D TMA box copy (cp.async.bulk.tensor) per 8 columns, plus a
+// 1-D box for the vector operand, into a ring of mbarrier-guarded stages; two groups of eight consumer
+// warps take alternate tiles (so that one group's latency-bound phases overlap the other's):
 //
 //   DOTS      out[c] = sum_i V[i,c]*x[i]                      (K6, + x.y for K5)
 //   UPD_SPEC  r = w - V*h ; ||r||^2 ; s[c] = sum_i V[i,c]*r[i]  (K7+K8 and, speculatively, the K9 dots:
 //             the tile is still in shared memory when r is known, so DGKS costs no extra pass over V)
 //   UPD       r -= V*s ; ||r||^2, predicated on the reference's test rnorm <= 0.717*wnorm (K9+K10)
+//   VQ        out(:,0:kout) = V(:,0:kin)*Q, optionally r = sigma*r + beta*out(:,c), ||r||^2 (K12-K16, K20)
 //
-// so a Lanczos/Arnoldi step reads V_j three times instead of the reference's four.
-// Rows beyond n and columns beyond j are zero-filled by the TMA unit (out-of-bounds boxes), which is
-// exactly the neutral element of every sum here.  Reductions are deterministic (fixed grid, fixed
-// trees, last-CTA combine).
-#include <cuda.h>
-
+// so a Lanczos/Arnoldi step reads V_j three times instead of the reference's four and
+// a restart reads V once.  Rows beyond n and columns beyond j are zero-filled by the TMA unit
+// (out-of-bounds boxes), the neutral element of every sum here.  Reductions are deterministic (fixed
+// grid, fixed trees, last-CTA combine).
+#include <cstdlib>
 #include <cstring>
 
+#include "tma_common.cuh"
 #include "vecops_cuda.cuh"
 
 namespace ab200 {
 
 namespace {
 
+using namespace ab200::tma;
+
 constexpr int R = 128;            // rows per tile == TMA box height
-constexpr int CB = 8;             // columns per TMA box == number of consumer warps
-constexpr int NCW = 8;            // consumer warps
+constexpr int CB = 8;             // columns per TMA box == warps per consumer group
+constexpr int NCW = 8;            // warps per consumer group
+constexpr int NG = 2;             // consumer groups (alternate tiles)
 constexpr int MAXB = 8;           // column boxes per tile -> j <= 64
 constexpr int MAXST = 12;         // ring depth limit
-constexpr int NG = 2;              // consumer groups (alternate tiles)
 constexpr int kThreadsTma = (NG * NCW + 1) * 32;
 constexpr uint32_t kTileBudget = 192 * 1024;
+constexpr uint32_t kTileBudgetVq = 188 * 1024;
 
 enum Mode { DOTS = 0, UPD = 1, UPD_SPEC = 2 };
 
@@ -39,6 +44,7 @@ struct OrthParams {
   int64_t n;
   int j, nboxes, nstages;
   uint32_t stage_bytes, box_bytes;
+  int x_tma;      // vector operand arrives through the TMA ring (needs a 16-byte aligned base)
   const T* x;     // DOTS: x            UPD*: src
   const T* y;     // DOTS: y (may alias x)
   T* dst;         // UPD*: destination (may alias src)
@@ -52,78 +58,9 @@ struct OrthParams {
   T* flag_out;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  uint32_t spins = 0;
-  long long t0 = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    // a lost TMA completion must surface as an error, never as a hung GPU: trap after ~10 s
-    if (!ok && ((++spins & 0xFFFu) == 0)) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000LL) __trap();
-    }
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
-
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-template <typename T>
-__device__ void finish_grid_reduce(T* partial, int pcols, int ncols, T* out, unsigned int* ticket) {
-  __shared__ bool s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  for (int c = warp; c < ncols; c += nwarps) {
-    T s = T(0);
-    for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partial + (size_t)b * pcols + c);
-    s = warp_sum(s);
-    if (lane == 0) out[c] = s;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
-}
-
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__ CUtensorMap tmap, const OrthParams<T> p) {
+__global__ void __launch_bounds__(kThreadsTma, 1)
+k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   if (MODE == UPD && p.pred_w2 != nullptr) {
     // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
@@ -146,7 +83,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
       mbar_init(full + s, 1);
       mbar_init(empty + s, NCW);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (MODE != DOTS)
     for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
@@ -154,6 +91,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
 
   const int64_t ntiles = (p.n + R - 1) / R;
   const uint32_t stage_elems = p.stage_bytes / sizeof(T);
+  const uint32_t v_bytes = (uint32_t)p.nboxes * p.box_bytes;  // the x tile sits right behind the V boxes
 
   if (warp == NG * NCW) {
     // ---------------- producer: one elected lane feeds the ring ----------------
@@ -163,27 +101,28 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
         const int s = it % p.nstages;
         const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
         mbar_wait(empty + s, ph ^ 1u);
-        mbar_expect_tx(full + s, (uint32_t)p.nboxes * p.box_bytes);
+        mbar_expect_tx(full + s, v_bytes + (p.x_tma ? (uint32_t)(R * sizeof(T)) : 0u));
         const uint32_t dst = smem_u32(tiles) + (uint32_t)s * p.stage_bytes;
-        for (int b = 0; b < p.nboxes; ++b) tma_load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
+        for (int b = 0; b < p.nboxes; ++b) load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
+        if (p.x_tma) load_1d(dst + v_bytes, &xmap, (int)(t * R), full + s);
       }
     }
   } else {
-    // ---------------- consumers: NG groups of NCW warps take alternate tiles, so that one group's
-    // latency-bound phases overlap the other's ----------------
+    // ---------------- consumers ----------------
     const int g = warp / NCW, gw = warp - g * NCW, gtid = tid - g * NCW * 32;
     T acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = T(0);
     T accn = T(0);
     const bool y_is_x = (p.y == p.x);
-    // the vector operand (4 rows per lane) is software-prefetched one tile ahead: its global-load
-    // latency would otherwise sit on the critical path of every tile
-    T xn[4];
+    // without TMA for the vector operand it is software-prefetched one tile ahead in registers
+    T xn[4] = {T(0), T(0), T(0), T(0)};
+    if (!p.x_tma) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int64_t r = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * R + lane + 32 * m;
-      xn[m] = (r < p.n) ? p.x[r] : T(0);
+      for (int m = 0; m < 4; ++m) {
+        const int64_t r = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * R + lane + 32 * m;
+        xn[m] = (r < p.n) ? p.x[r] : T(0);
+      }
     }
     int it = g;
     for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
@@ -191,11 +130,20 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
       const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
       const int64_t row0 = t * R;
       T xv[4];
+      if (!p.x_tma) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        xv[m] = xn[m];
-        const int64_t r = row0 + (int64_t)NG * gridDim.x * R + lane + 32 * m;
-        xn[m] = (r < p.n) ? p.x[r] : T(0);
+        for (int m = 0; m < 4; ++m) {
+          xv[m] = xn[m];
+          const int64_t r = row0 + (int64_t)NG * gridDim.x * R + lane + 32 * m;
+          xn[m] = (r < p.n) ? p.x[r] : T(0);
+        }
+      }
+      mbar_wait(full + s, ph);
+      const T* tile = tiles + (size_t)s * stage_elems;
+      if (p.x_tma) {
+        const T* xs = tile + v_bytes / sizeof(T);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) xv[m] = xs[lane + 32 * m];
       }
       if (MODE == DOTS && gw == 0) {
         if (y_is_x) {
@@ -209,8 +157,6 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
           }
         }
       }
-      mbar_wait(full + s, ph);
-      const T* tile = tiles + (size_t)s * stage_elems;
       if (MODE != DOTS) {
         // phase 1: row-local product V(i,:)*coef, columns split in two interleaved halves
         const int row = gtid & (R - 1), half = gtid >> 7;
@@ -286,91 +232,194 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_orth(const __grid_constant__
   finish_grid_reduce(p.partial, p.pcols, (MODE == UPD) ? 1 : p.j + 1, p.out, p.ticket);
 }
 
-// ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
-
-// Descriptors depend only on (base, n, ldv, columns, element size); a solve cycles through at most ncv
-// of them, so they are encoded once and reused (the encode call is a driver round trip).
-struct TmapEntry {
-  const void* v;
-  int64_t n, ldv;
-  int ncols, esize;
-  CUtensorMap map;
+// ---------------------------------------------------------------------------------------------
+// VQ: out(:,0:kout) = V(:,0:kin) * Q.  Each consumer group owns a 128-row tile; a warp computes a
+// register block of (32*RPL rows) x (4 columns): RPL V values per lane and four Q entries (broadcast
+// from shared memory) feed 4*RPL FP64 FMAs per k, which keeps the shared-memory traffic below the HBM
+// time of the tile.  out may alias V (the tile is complete in shared memory before anything is written).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct VqParams {
+  int64_t n, ldo;
+  int kin, kout, kp;  // kp = kout rounded up to a multiple of 4 (zero-padded Q columns)
+  int nboxes, nstages, rpl_items;  // rpl_items = number of (row slice, column group) work items
+  uint32_t stage_bytes, box_bytes;
+  const T* q;  // device, packed column-major kin x kout
+  T* out;
+  int with_resid, beta_col;
+  T sigma, beta;
+  T* resid;
+  T* partial;
+  T* nrm2_out;
+  unsigned int* ticket;
 };
-template <typename T>
-bool make_tmap_uncached(CUtensorMap* map, const T* v, int64_t n, int64_t ldv, int ncols);
-std::vector<TmapEntry>& tmap_cache() {
-  static std::vector<TmapEntry> c;
-  return c;
-}
 
 template <typename T>
-bool make_tmap(CUtensorMap* map, const T* v, int64_t n, int64_t ldv, int ncols) {
-  auto& cache = tmap_cache();
-  for (const TmapEntry& e : cache) {
-    if (e.v == v && e.n == n && e.ldv == ldv && e.ncols == ncols && e.esize == (int)sizeof(T)) {
-      *map = e.map;
-      return true;
+__device__ __forceinline__ void load4(const T* p, T (&q)[4]);
+template <>
+__device__ __forceinline__ void load4<double>(const double* p, double (&q)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+}
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&q)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
+}
+
+template <typename T, int RPL>
+__global__ void __launch_bounds__(kThreadsTma, 1) k_vq_tma(const __grid_constant__ CUtensorMap tmap, const VqParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* tiles = reinterpret_cast<T*>(smem);
+  unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
+  T* qs = reinterpret_cast<T*>(aux);                          // [kin][kp]
+  T* red = qs + (size_t)MAXB * CB * MAXB * CB;                // [NG*NCW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + NG * NCW + 8);
+  uint64_t* empty = full + MAXST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NCW);
     }
+    mbar_fence_init();
   }
-  if (!make_tmap_uncached<T>(map, v, n, ldv, ncols)) return false;
-  if (cache.size() >= 512) cache.clear();
-  cache.push_back(TmapEntry{v, n, ldv, ncols, (int)sizeof(T), *map});
-  return true;
+  for (int i = tid; i < p.kin * p.kp; i += kThreadsTma) {
+    const int k = i / p.kp, c = i - k * p.kp;
+    qs[i] = (c < p.kout) ? p.q[(size_t)c * p.kin + k] : T(0);
+  }
+  if (tid < NG * NCW + 8) red[tid] = T(0);
+  __syncthreads();
+  const int64_t ntiles = (p.n + R - 1) / R;
+  const uint32_t stage_elems = p.stage_bytes / sizeof(T);
+  T nrm = T(0);
+  if (warp == NG * NCW) {
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % p.nstages;
+        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        mbar_expect_tx(full + s, (uint32_t)p.nboxes * p.box_bytes);
+        const uint32_t dst = smem_u32(tiles) + (uint32_t)s * p.stage_bytes;
+        for (int b = 0; b < p.nboxes; ++b) load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
+      }
+    }
+  } else {
+    const int g = warp / NCW, gw = warp - g * NCW;
+    constexpr int NRS = 4 / RPL;  // row slices of 32*RPL rows per tile
+    int it = g;
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
+      const int s = it % p.nstages;
+      const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+      const int64_t row0 = t * R;
+      mbar_wait(full + s, ph);
+      const T* tile = tiles + (size_t)s * stage_elems;
+      for (int item = gw; item < p.rpl_items; item += NCW) {
+        const int rs = item % NRS, cg = item / NRS;
+        const T* tv = tile + rs * 32 * RPL + lane;
+        const T* qrow = qs + cg * 4;
+        T acc[RPL][4];
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[m][c] = T(0);
+#pragma unroll 2
+        for (int k = 0; k < p.kin; ++k) {
+          T qv[4];
+          load4<T>(qrow + (size_t)k * p.kp, qv);
+          T vv[RPL];
+#pragma unroll
+          for (int m = 0; m < RPL; ++m) vv[m] = tv[(size_t)k * R + 32 * m];
+#pragma unroll
+          for (int m = 0; m < RPL; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[m][c] += vv[m] * qv[c];
+        }
+        // every warp of the group must have finished reading the tile before anyone overwrites V when
+        // out aliases V: writes only touch this tile's rows, which no other tile reads, and the tile
+        // itself lives in shared memory, so no further synchronisation is needed
+#pragma unroll
+        for (int m = 0; m < RPL; ++m) {
+          const int64_t r = row0 + rs * 32 * RPL + lane + 32 * m;
+          if (r < p.n) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int col = cg * 4 + c;
+              if (col < p.kout) p.out[r + (int64_t)col * p.ldo] = acc[m][c];
+              if (p.with_resid && col == p.beta_col) {
+                const T v = p.sigma * p.resid[r] + p.beta * acc[m][c];
+                p.resid[r] = v;
+                nrm += v * v;
+              }
+            }
+            if (p.with_resid && p.beta_col < 0 && cg == 0) {
+              const T v = p.sigma * p.resid[r];
+              p.resid[r] = v;
+              nrm += v * v;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    nrm = warp_sum(nrm);
+    if (lane == 0) red[warp] = nrm;
+  }
+  if (!p.with_resid || p.nrm2_out == nullptr) return;
+  __syncthreads();
+  if (tid == 0) {
+    T sum = T(0);
+#pragma unroll
+    for (int w = 0; w < NG * NCW; ++w) sum += red[w];
+    p.partial[blockIdx.x] = sum;
+  }
+  finish_grid_reduce(p.partial, 1, 1, p.nrm2_out, p.ticket);
 }
 
-template <typename T>
-bool make_tmap_uncached(CUtensorMap* map, const T* v, int64_t n, int64_t ldv, int ncols) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)ncols};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ldv * sizeof(T)};
-  const cuuint32_t box[2] = {(cuuint32_t)R, (cuuint32_t)CB};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                        const_cast<T*>(v), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
+// ---- host side -------------------------------------------------------------------------------
 template <typename T>
 size_t aux_bytes() {
   return sizeof(T) * (NG * 4 * R + 2 * MAXB * CB + 8) + sizeof(uint64_t) * 2 * MAXST;
 }
+template <typename T>
+size_t aux_bytes_vq() {
+  return sizeof(T) * ((size_t)MAXB * CB * MAXB * CB + NG * NCW + 8) + sizeof(uint64_t) * 2 * MAXST;
+}
 
 template <typename T>
-void geometry(int j, OrthParams<T>& p) {
+void geometry(int j, bool x_tma, OrthParams<T>& p) {
   p.j = j;
   p.nboxes = (j + CB - 1) / CB;
   p.box_bytes = (uint32_t)(R * CB * sizeof(T));
-  p.stage_bytes = (uint32_t)p.nboxes * p.box_bytes;
+  static const bool allow_xtma = !(getenv("AB200_XTMA") && std::strcmp(getenv("AB200_XTMA"), "0") == 0);
+  x_tma = x_tma && allow_xtma;
+  p.x_tma = x_tma ? 1 : 0;
+  // the vector tile (R elements) rides behind the V boxes; stages stay 128-byte aligned
+  p.stage_bytes = (uint32_t)p.nboxes * p.box_bytes + (x_tma ? (uint32_t)(R * sizeof(T)) : 0u);
   int ns = (int)(kTileBudget / p.stage_bytes);
   p.nstages = ns > MAXST ? MAXST : (ns < 2 ? 2 : ns);
+  static const int force_max = getenv("AB200_MAXST") ? atoi(getenv("AB200_MAXST")) : 0;
+  if (force_max > 1 && p.nstages > force_max) p.nstages = force_max;
+  // The ring depth must be a multiple of the number of consumer groups: tile `it` goes to group it % NG
+  // and to stage it % nstages, so only then does every stage (and its pair of mbarriers) belong to ONE
+  // group, which therefore observes every phase of it.  With an odd depth a group would see every
+  // other phase of a barrier and the parity test of mbarrier.try_wait could be satisfied by the
+  // previous-but-one completion (observed on the B200: sporadic launch failures).
+  p.nstages -= p.nstages % NG;
 }
 
 template <typename T, int MODE>
 bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, OrthParams<T>& p, const char* name,
                  double bytes) {
-  CUtensorMap map;
-  if (!make_tmap<T>(&map, v, p.n, ldv, p.j)) return false;
+  CUtensorMap map, xmap;
+  if (!get_tensor_map(&map, v, (int)sizeof(T), p.n, ldv, p.j, R, CB)) return false;
+  if (p.x_tma) {
+    if (!get_tensor_map(&xmap, p.x, (int)sizeof(T), p.n, 0, 0, R, 0)) return false;
+  } else {
+    xmap = map;
+  }
   static bool attr_set = false;
   const size_t smem = (size_t)p.nstages * p.stage_bytes + aux_bytes<T>();
   if (!attr_set) {
@@ -384,12 +433,14 @@ bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, Orth
   const int64_t ntiles = (p.n + R - 1) / R;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   ProfScope ps(stream, name, bytes);
-  k_orth<T, MODE><<<grid, kThreadsTma, smem, stream>>>(map, p);
+  k_orth<T, MODE><<<grid, kThreadsTma, smem, stream>>>(map, xmap, p);
   launch_stats().kernels++;
   launch_stats().fast_path++;
   AB200_CUDA_CHECK(cudaGetLastError());
   return true;
 }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
@@ -399,17 +450,17 @@ struct CudaVecOps<T>::TmaCache {};
 template <typename T>
 bool CudaVecOps<T>::fast_path_ok(int64_t n, int j, const T* v, int64_t ldv) const {
   if (j < 1 || j > MAXB * CB || n < 1) return false;
-  if ((reinterpret_cast<uintptr_t>(v) & 15u) != 0) return false;       // TMA: 16-byte aligned base ...
+  if (!aligned16(v)) return false;                                     // TMA: 16-byte aligned base ...
   if (((size_t)ldv * sizeof(T)) % 16 != 0) return false;               // ... and column stride
   if (n > 2147483647LL - R) return false;                              // TMA coordinates are int32
-  return encode_fn() != nullptr;
+  return tensor_maps_available();
 }
 
 template <typename T>
 bool CudaVecOps<T>::dots_tma(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* out) {
   OrthParams<T> p{};
   p.n = n;
-  geometry<T>(j, p);
+  geometry<T>(j, aligned16(x), p);
   const int grid = (int)std::min<int64_t>((n + R - 1) / R, num_sms_);
   p.pcols = j + 1;
   ensure_partial((size_t)grid * p.pcols);
@@ -427,7 +478,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
   {
     OrthParams<T> p{};
     p.n = n;
-    geometry<T>(j, p);
+    geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
     p.x = w; p.y = w; p.partial = partial_; p.out = mbA; p.ticket = ticket_;
     if (!launch_orth<T, DOTS>(stream_, num_sms_, v, ldv, p, "dots_tma", (double)sizeof(T) * n * (j + 1.0)))
@@ -438,7 +489,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
   {
     OrthParams<T> p{};
     p.n = n;
-    geometry<T>(j, p);
+    geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
     p.x = w; p.dst = resid; p.coef = mbA; p.partial = partial_; p.out = mbB; p.ticket = ticket_;
     if (!launch_orth<T, UPD_SPEC>(stream_, num_sms_, v, ldv, p, "update_spec_tma", (double)sizeof(T) * n * (j + 2.0)))
@@ -449,7 +500,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
   {
     OrthParams<T> p{};
     p.n = n;
-    geometry<T>(j, p);
+    geometry<T>(j, aligned16(resid), p);
     p.pcols = 1;
     p.x = resid; p.dst = resid; p.coef = mbB; p.partial = partial_; p.out = mbC; p.ticket = ticket_;
     p.pred_w2 = mbA + j; p.pred_r2 = mbB + j; p.flag_out = mbC + 1;
@@ -461,8 +512,54 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
 }
 
 template <typename T>
-bool CudaVecOps<T>::vq_tma(int64_t, int, int, const T*, int64_t, const T*, T*, int64_t, bool, T, T, int, T*, T*) {
-  return false;  // the restart update still runs the generic kernel (2-3 % of the traffic)
+bool CudaVecOps<T>::vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* qdev, T* out, int64_t ldo,
+                           bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2) {
+  if (kin < 1 || kin > MAXB * CB || kout < 1 || kout > MAXB * CB) return false;
+  if (!fast_path_ok(n, kin, v, ldv)) return false;
+  VqParams<T> p{};
+  p.n = n; p.ldo = ldo; p.kin = kin; p.kout = kout; p.kp = (kout + 3) & ~3;
+  p.nboxes = (kin + CB - 1) / CB;
+  p.box_bytes = (uint32_t)(R * CB * sizeof(T));
+  p.stage_bytes = (uint32_t)p.nboxes * p.box_bytes;
+  int ns = (int)(kTileBudgetVq / p.stage_bytes);
+  p.nstages = ns > MAXST ? MAXST : (ns < 2 ? 2 : ns);
+  p.nstages -= p.nstages % NG;  // see geometry(): one consumer group per stage
+  p.q = qdev; p.out = out;
+  p.with_resid = with_resid ? 1 : 0; p.beta_col = beta_col; p.sigma = sigma; p.beta = beta; p.resid = resid;
+  p.nrm2_out = mb_nrm2; p.ticket = ticket_;
+  const int ncg = p.kp / 4;
+  // rows per lane: enough (row slice x column group) items to occupy the 8 warps of a group
+  const int rpl = (ncg >= 8) ? 4 : (ncg >= 4) ? 2 : 1;
+  p.rpl_items = (4 / rpl) * ncg;
+  CUtensorMap map;
+  if (!get_tensor_map(&map, v, (int)sizeof(T), n, ldv, kin, R, CB)) return false;
+  const int64_t ntiles = (n + R - 1) / R;
+  const int grid = (int)(ntiles < num_sms_ ? ntiles : num_sms_);
+  ensure_partial((size_t)grid);
+  p.partial = partial_;
+  const size_t smem = (size_t)p.nstages * p.stage_bytes + aux_bytes_vq<T>();
+  const int smem_max = (int)(kTileBudgetVq + aux_bytes_vq<T>());
+  static bool attr_set[3] = {false, false, false};
+  const int ai = rpl == 4 ? 2 : (rpl == 2 ? 1 : 0);
+  if (!attr_set[ai]) {
+    cudaError_t e = cudaSuccess;
+    if (rpl == 4) e = cudaFuncSetAttribute(k_vq_tma<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    else if (rpl == 2) e = cudaFuncSetAttribute(k_vq_tma<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    else e = cudaFuncSetAttribute(k_vq_tma<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set[ai] = true;
+  }
+  ProfScope ps(stream_, "vq_tma", (double)sizeof(T) * n * (kin + kout + (with_resid ? 2.0 : 0.0)));
+  if (rpl == 4) k_vq_tma<T, 4><<<grid, kThreadsTma, smem, stream_>>>(map, p);
+  else if (rpl == 2) k_vq_tma<T, 2><<<grid, kThreadsTma, smem, stream_>>>(map, p);
+  else k_vq_tma<T, 1><<<grid, kThreadsTma, smem, stream_>>>(map, p);
+  launch_stats().kernels++;
+  launch_stats().fast_path++;
+  AB200_CUDA_CHECK(cudaGetLastError());
+  return true;
 }
 template <typename T>
 void CudaVecOps<T>::tma_release() {}

@@ -137,6 +137,12 @@ void ab200_reset_seed(void);
 void ab200_profile_enable(int on);
 void ab200_profile_reset(void);
 int ab200_profile_get(int idx, char* name64, double* ms, unsigned long long* launches, double* bytes);
+/* kernel unit-test hooks: one fused orthogonalisation step (K4..K10) / one restart update (K12..K16) on caller-supplied
+ * DEVICE arrays; out_host gets [h(0..j-1), ||w||^2, s(0..j-1), ||r||^2, ||r'||^2, dgks_flag] */
+int ab200_debug_orth_f64(long long n, int j, const double* v, long long ldv, const double* w, double* resid,
+                         double* out_host);
+int ab200_debug_vq_f64(long long n, int kin, int kout, double* v, long long ldv, const double* q_host, double sigma,
+                       double beta, int beta_col, double* resid, double* nrm2_host);
 /* kernel micro-benchmark on synthetic data (tools/kernel_sweep.py): what = 0 orth step, 1 multi-dots, 2 V*Q update */
 int ab200_kernel_probe_f64(long long n, int j, int ncv, int iters, int what, int kout);
 int ab200_device_count(void);
