@@ -445,3 +445,12 @@ def nccl_comm_from_torch_distributed():
     if h < 1:
         raise ArpackB200Error(f"ab200_comm_create failed ({h})")
     return h
+
+
+def slab_partition(nlines, world, rank):
+    """PARPACK-style block-row layout (dsaupd.f:331-349; icb_parpack_c.c:60-69): `nlines` grid lines/planes split
+    over `world` ranks, the remainder spread over the first ranks.  Returns (first line, number of lines)."""
+    base, rem = divmod(nlines, world)
+    cnt = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, cnt
