@@ -137,14 +137,16 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
 
 // nnz of a CSR matrix whose rowptr lives on the device, cached per rowptr address
 long long nnz_of(int nrows, const int* rowptr) {
-  static const int* last_ptr = nullptr;
-  static int last_rows = 0;
-  static long long last_nnz = 0;
-  if (rowptr == last_ptr && nrows == last_rows) return last_nnz;
+  struct Entry { const int* ptr; int rows; long long nnz; };
+  static Entry cache[8] = {};
+  static int next = 0;
+  for (const Entry& e : cache)
+    if (e.ptr == rowptr && e.rows == nrows) return e.nnz;
   int h = 0;
   if (cudaMemcpyAsync(&h, rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, cur_stream()) != cudaSuccess) return 0;
   cudaStreamSynchronize(cur_stream());
-  last_ptr = rowptr; last_rows = nrows; last_nnz = h;
+  cache[next] = Entry{rowptr, nrows, (long long)h};
+  next = (next + 1) % 8;
   return h;
 }
 

@@ -153,6 +153,13 @@ def run_reference(args):
 
 
 def workload_config(args, restarts):
+    if getattr(args, "workload", "laplace2d") == "laplace3d":
+        e = args.nx
+        return {"workload": f"BASELINE config 3: pdsaupd-style solve on 3-D 7-point Laplacian {e}^3 (n={e ** 3}) CSR FP64, "
+                            f"z-slab row partition, nev=20 ncv=64 which=LA tol={TOL}, fixed restart budget",
+                "nx": e, "n": e ** 3, "nev": 20, "ncv": 64, "which": "LA", "tol": TOL, "restarts_per_step": restarts,
+                "start_vector": "splitmix64 hash, info=1",
+                "l2": "inputs larger than L2 (V alone is %.1f GB)" % (e ** 3 * 64 * 8 / 1e9)}
     return {"workload": f"BASELINE config 2: dsaupd on 2-D 5-point Laplacian {args.nx}x{args.nx} (n={args.nx * args.nx}) "
                         f"CSR FP64, nev={NEV} ncv={NCV} which={WHICH} tol={TOL}, fixed restart budget",
             "nx": args.nx, "n": args.nx * args.nx, "nev": NEV, "ncv": NCV, "which": WHICH, "tol": TOL,
@@ -180,23 +187,29 @@ def run_ours(args):
         comm = ab.nccl_comm_from_torch_distributed()
     L = ab.lib()
     nx = args.nx
-    n_global = nx * nx
-    # row (y-slab) partition, PARPACK's block-row layout (dsaupd.f:331-349)
+    nev, ncv = NEV, NCV
+    # block-row partition, PARPACK's layout (dsaupd.f:331-349): y-slabs of the 2-D grid / z-slabs of the 3-D grid
     y0, nyloc = ab.slab_partition(nx, world, rank)
-    if world == 1:
+    if args.workload == "laplace3d":
+        nev, ncv = 20, 64
+        A = ab.CsrOperator.laplace3d(nx, nx, nx, z0=y0, nzloc=nyloc)
+        r0 = ab.hashed_start_vector(A.n, i0=y0 * nx * nx)
+    elif world == 1:
         A = ab.CsrOperator.laplace2d(nx, nx)
-        op = A
+        r0 = ab.hashed_start_vector(A.n)
     else:
         A = ab.CsrOperator.laplace3d(nx, 1, nx, z0=y0, nzloc=nyloc, diag=4.0)
-
+        r0 = ab.hashed_start_vector(A.n, i0=y0 * nx)
+    if world == 1:
+        op = A
+    else:
         def op(x, y, *_):
             A.apply_halo(comm, x, y)
     n = A.n
-    r0 = ab.hashed_start_vector(n, i0=y0 * nx)
     restarts = args.restarts
 
     def one_solve(host_buffers=False, resid=None):
-        return ab.solve(op, n, NEV, NCV, WHICH, tol=TOL, mxiter=restarts, resid=resid if resid is not None else r0,
+        return ab.solve(op, n, nev, ncv, WHICH, tol=TOL, mxiter=restarts, resid=resid if resid is not None else r0,
                         eupd=False, host_buffers=host_buffers, comm=comm)
 
     def barrier():
@@ -250,7 +263,7 @@ def run_ours(args):
         w = 8
         # library: H2D resid once; per hand-off D2H x + H2D y; at ido=99 D2H V + resid.  OP: H2D x + D2H y per call
         h2d = n * w + per * (n * w) + per * (n * w)
-        d2h = per * (n * w) + per * (n * w) + n * NCV * w + n * w
+        d2h = per * (n * w) + per * (n * w) + n * ncv * w + n * w
         e2e = {"value": nop2 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "bench_steps": e2e_steps, "buffers": "pinned host resid/V/workd, OP = H2D + CSR SpMV kernel + D2H"}
 
@@ -315,6 +328,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--restarts", type=int, default=4)
+    ap.add_argument("--workload", default="laplace2d", choices=["laplace2d", "laplace3d"],
+                    help="laplace2d = BASELINE config 2 (default, the headline); laplace3d = config 3 (use --nx 512)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
