@@ -95,16 +95,20 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
 
   if (warp == NG * NCW) {
     // ---------------- producer: one elected lane feeds the ring ----------------
+    // stage / phase are kept incrementally: no division on the critical path
+    // (issuing the boxes from several lanes was measured slower: UTMALDG takes uniform-register operands, so the
+    // compiler serialises per-lane issues; one elected lane issuing back to back is the fast form)
     if (lane == 0) {
-      int it = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % p.nstages;
-        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = v_bytes + (p.x_tma ? (uint32_t)(R * sizeof(T)) : 0u);
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         mbar_wait(empty + s, ph ^ 1u);
-        mbar_expect_tx(full + s, v_bytes + (p.x_tma ? (uint32_t)(R * sizeof(T)) : 0u));
+        mbar_expect_tx(full + s, tx_bytes);
         const uint32_t dst = smem_u32(tiles) + (uint32_t)s * p.stage_bytes;
         for (int b = 0; b < p.nboxes; ++b) load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
         if (p.x_tma) load_1d(dst + v_bytes, &xmap, (int)(t * R), full + s);
+        if (++s == p.nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -124,10 +128,9 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         xn[m] = (r < p.n) ? p.x[r] : T(0);
       }
     }
-    int it = g;
-    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
-      const int s = it % p.nstages;
-      const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+    int s = g, kt = 0;  // stage of my current tile (nstages is a multiple of NG), count of my tiles
+    uint32_t ph = 0;
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, ++kt) {
       const int64_t row0 = t * R;
       T xv[4];
       if (!p.x_tma) {
@@ -169,7 +172,7 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
           a1 += tr[(c + 2) * R] * cs[c + 2];
         }
         if (c < p.j) a0 += tr[c * R] * cs[c];
-        T* psb = ps + g * 4 * R + ((it / NG) & 1) * 2 * R;
+        T* psb = ps + g * 4 * R + (kt & 1) * 2 * R;
         psb[half * R + row] = a0 + a1;
         if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(NCW * 32) : "memory");
@@ -200,6 +203,8 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
+      s += NG;
+      if (s >= p.nstages) { s -= p.nstages; ph ^= 1u; }
     }
     // per-CTA partials: group 1 parks its warp sums in shared memory, group 0 adds its own and publishes
     T* mine = p.partial + (size_t)blockIdx.x * p.pcols;
@@ -295,23 +300,22 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_vq_tma(const __grid_constant
   T nrm = T(0);
   if (warp == NG * NCW) {
     if (lane == 0) {
-      int it = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % p.nstages;
-        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         mbar_wait(empty + s, ph ^ 1u);
         mbar_expect_tx(full + s, (uint32_t)p.nboxes * p.box_bytes);
         const uint32_t dst = smem_u32(tiles) + (uint32_t)s * p.stage_bytes;
         for (int b = 0; b < p.nboxes; ++b) load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
+        if (++s == p.nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
     const int g = warp / NCW, gw = warp - g * NCW;
     constexpr int NRS = 4 / RPL;  // row slices of 32*RPL rows per tile
-    int it = g;
-    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
-      const int s = it % p.nstages;
-      const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+    int s = g;
+    uint32_t ph = 0;
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x) {
       const int64_t row0 = t * R;
       mbar_wait(full + s, ph);
       const T* tile = tiles + (size_t)s * stage_elems;
@@ -363,6 +367,8 @@ __global__ void __launch_bounds__(kThreadsTma, 1) k_vq_tma(const __grid_constant
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
+      s += NG;
+      if (s >= p.nstages) { s -= p.nstages; ph ^= 1u; }
     }
     nrm = warp_sum(nrm);
     if (lane == 0) red[warp] = nrm;
