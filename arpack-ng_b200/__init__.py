@@ -87,6 +87,10 @@ def lib():
     L.ab200_release.argtypes = [vp]
     L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.ab200_device_count.restype = C.c_int
+    L.ab200_register_csr_op_f64.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
+    L.ab200_register_csr_op_f32.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
+    L.ab200_fused_dot_maxdiff.argtypes = [vp]
+    L.ab200_fused_dot_maxdiff.restype = C.c_double
     L.ab200_kernel_probe_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ab200_debug_orth_f64.argtypes = [C.c_longlong, C.c_int, vp, C.c_longlong, vp, vp, vp]
     L.ab200_debug_vq_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_double, C.c_double,
@@ -224,7 +228,7 @@ class Result(dict):
 
 def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.float64,
           bop=None, rvec=True, sigma=0.0, sigmai=0.0, device="cuda", host_buffers=False, comm=None, ishift=1,
-          eupd=True, pinned=True):
+          eupd=True, pinned=True, registered_op=None):
     """Run a whole *aupd/*eupd solve through the C-ABI.
 
     device arrays (default): resid/v/workd are torch CUDA tensors; ``op(x, y)`` receives tensor views of the
@@ -261,6 +265,16 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             info[0] = 1
         else:
             res = torch.zeros(n, dtype=t_dt, device=device)
+    if registered_op is not None:
+        # opt-in extension: the library applies the CSR operator itself (one *aupd call per solve)
+        if registered_op.val.dtype != t_dt:
+            raise ArpackB200Error("registered_op values must have the solve's dtype")
+        reg = L.ab200_register_csr_op_f64 if np_dt == np.float64 else L.ab200_register_csr_op_f32
+        if reg(workl.ctypes.data, registered_op.n, registered_op.nnz, registered_op.rowptr.data_ptr(),
+               registered_op.col.data_ptr(), registered_op.val.data_ptr()) != 0:
+            raise ArpackB200Error("register_csr_op failed")
+        if op is None:
+            op = registered_op
     aupd = dsaupd_c if sym else dnaupd_c
     nsteps = 0
     while True:
@@ -278,7 +292,8 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
         else:
             break
     out = Result(info=int(info[0]), iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v, resid=res,
-                 nconv=int(iparam[4]), nsteps=nsteps, workd=workd)
+                 nconv=int(iparam[4]), nsteps=nsteps, workd=workd,
+                 fused_dot_maxdiff=(L.ab200_fused_dot_maxdiff(workl.ctypes.data) if registered_op is not None else None))
     if info[0] < 0 or not eupd:
         return out
     select = np.zeros(ncv, dtype=np.int32)
@@ -379,8 +394,10 @@ class CsrOperator:
             rc = L.ab200_csr_spmv_hostvec_f64(self.n, self.ncols, self.rowptr.data_ptr(), self.col.data_ptr(),
                                               self.val.data_ptr(), x.ctypes.data, y.ctypes.data)
         else:
-            rc = L.ab200_csr_spmv_f64(self.n, self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(),
-                                      x.data_ptr(), y.data_ptr())
+            import torch
+            f = L.ab200_csr_spmv_f64 if self.val.dtype == torch.float64 else L.ab200_csr_spmv_f32
+            rc = f(self.n, self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), x.data_ptr(),
+                   y.data_ptr())
         if rc != 0:
             raise ArpackB200Error(f"csr_spmv failed ({rc})")
 

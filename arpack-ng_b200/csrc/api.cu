@@ -24,6 +24,7 @@
 #include <unordered_map>
 
 #include "../../include/arpack_b200.h"
+#include "driver.hpp"
 #include "irl_nonsym.hpp"
 #include "irl_sym.hpp"
 #include "vecops_cuda.cuh"
@@ -141,6 +142,36 @@ Ctx<T>* make_ctx(const void* key, bool par, int comm_handle, int n, int ncv, T* 
   return raw;
 }
 
+// operators registered for the solve keyed to a workl address (picked up at ido = 0)
+template <typename T>
+std::unordered_map<const void*, CsrOpDesc<T>>& registered_ops() {
+  static std::unordered_map<const void*, CsrOpDesc<T>> t;
+  return t;
+}
+
+template <typename T, typename Solver>
+void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
+  CsrOpDesc<T> d;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = registered_ops<T>().find(key);
+    if (it == registered_ops<T>().end()) return;
+    d = it->second;
+  }
+  if (d.nrows != n) throw CudaError("registered CSR operator has a different row count than the solve");
+  CudaVecOps<T>* ops = c->ops.get();
+  solver->set_registered_op(
+      [d](const T* x, T* y) {
+        if (csr_op_apply<T>(d, x, y) != 0) throw CudaError("registered CSR operator: SpMV launch failed");
+      },
+      [d, ops](T inv, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+        const int rc = csr_op_apply_fused<T>(d, inv, resid, vj, y, ops->reduction_scratch(2 * 148 * 16), mb_dots,
+                                             ops->reduction_ticket());
+        if (rc < 0) throw CudaError("registered CSR operator: fused SpMV launch failed");
+        return rc == 0;
+      });
+}
+
 template <typename T>
 Ctx<T>* find_ctx(const void* key) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -167,6 +198,10 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
       SeedState* seed = par ? &Globals<T>::seed_par : &Globals<T>::seed;
       if (SYM) c->sym = std::make_unique<IrlSym<T>>(c->ops.get(), par, seed);
       else c->nonsym = std::make_unique<IrlNonsym<T>>(c->ops.get(), par, seed, &Globals<T>::smlnum_first);
+      if (!par && iparam[6] == 1 && bmat[0] == 'I') {
+        if (SYM) attach_registered_op<T>(c, c->sym.get(), workl, n);
+        else attach_registered_op<T>(c, c->nonsym.get(), workl, n);
+      }
       if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
     } else {
       c = find_ctx<T>(workl);
@@ -476,6 +511,8 @@ void ab200_release(const void* workl) {
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().erase(workl);
   table<float>().erase(workl);
+  registered_ops<double>().erase(workl);
+  registered_ops<float>().erase(workl);
 }
 void ab200_release_all(void) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -490,6 +527,40 @@ void ab200_reset_seed(void) {
   Globals<double>::seed = SeedState(); Globals<double>::seed_par = SeedState();
   Globals<float>::seed = SeedState(); Globals<float>::seed_par = SeedState();
   Globals<double>::smlnum_first = -1.0; Globals<float>::smlnum_first = -1.0f;
+}
+// Registered-operator mode: y = A x for a square CSR matrix resident in HBM is applied by the
+// library itself for the solve keyed to `workl` (mode 1, bmat = 'I'), so *aupd_c never returns ido = +-1 and one call
+// runs the whole solve; start-of-step scaling and the alpha / ||w||^2 dots are fused into the SpMV kernel.
+// nrows = 0 removes the registration.
+int ab200_register_csr_op_f64(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
+                              const double* val) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (nrows <= 0) { registered_ops<double>().erase(workl); return 0; }
+  CsrOpDesc<double> d;
+  d.nrows = nrows; d.nnz = nnz; d.rowptr = rowptr; d.col = col; d.val = val;
+  registered_ops<double>()[workl] = d;
+  return 0;
+}
+int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
+                              const float* val) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (nrows <= 0) { registered_ops<float>().erase(workl); return 0; }
+  CsrOpDesc<float> d;
+  d.nrows = nrows; d.nnz = nnz; d.rowptr = rowptr; d.col = col; d.val = val;
+  registered_ops<float>()[workl] = d;
+  return 0;
+}
+// largest relative disagreement between the SpMV-epilogue dots and the CGS sweep in the last registered-op solve
+double ab200_fused_dot_maxdiff(const void* workl) {
+  if (Ctx<double>* c = find_ctx<double>(workl)) {
+    if (c->sym) return (double)c->sym->fused_dot_maxdiff;
+    if (c->nonsym) return (double)c->nonsym->fused_dot_maxdiff;
+  }
+  if (Ctx<float>* c = find_ctx<float>(workl)) {
+    if (c->sym) return (double)c->sym->fused_dot_maxdiff;
+    if (c->nonsym) return (double)c->nonsym->fused_dot_maxdiff;
+  }
+  return -1.0;
 }
 void ab200_profile_enable(int on) { profiler().enabled = (on != 0); }
 void ab200_profile_reset(void) { profiler().reset(); }

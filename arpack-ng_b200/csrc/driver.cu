@@ -12,6 +12,8 @@
 #include <cstring>
 
 #include "../../include/arpack_b200.h"
+#include "driver.hpp"
+#include "tma_common.cuh"
 #include "vecops_cuda.cuh"
 
 namespace ab200 {
@@ -56,19 +58,30 @@ __global__ void __launch_bounds__(256) k_csr_spmv(int nrows, const int* __restri
 // independent col/val loads and four x gathers in flight per thread), parks the products in shared
 // memory, then every thread sums its own row in order.  Only two dependent memory levels per entry
 // instead of the three of the row-per-sub-warp kernel, and deterministic row sums.
-template <typename T, int ROWS, int CAP>
+//
+// FUSED (registered-operator mode of the solver, square A): the operand is xs*x with x = the
+// unnormalised residual and xs = 1/||r|| (K1/K2 folded into K3: v_j = xs*x is written on the way, the
+// scaled copies of x are never materialised), and the epilogue accumulates alpha = v_j^T (A v_j) and
+// ||A v_j||^2 into dots_out[0..1] (north_star: "alpha = v^T w fused into the SpMV epilogue").
+template <typename T, int ROWS, int CAP, bool FUSED>
 __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* __restrict__ rowptr,
                                                           const int* __restrict__ col, const T* __restrict__ val,
                                                           const T* __restrict__ x, T* __restrict__ y, int nloc,
-                                                          const T* __restrict__ xh) {
+                                                          const T* __restrict__ xh, T xs, T* __restrict__ vj_out,
+                                                          T* __restrict__ partial, T* __restrict__ dots_out,
+                                                          unsigned int* ticket) {
   __shared__ T prod[CAP];
   __shared__ int srow[ROWS + 1];
+  __shared__ T red[2][ROWS / 32];
   const int tid = threadIdx.x;
+  T dxy = T(0), dyy = T(0);
   for (long long blk = blockIdx.x; blk * ROWS < nrows; blk += gridDim.x) {
     const int r0 = (int)(blk * ROWS);
     const int nr = (nrows - r0 < ROWS) ? (nrows - r0) : ROWS;
     if (tid < nr) srow[tid] = rowptr[r0 + tid];
     if (tid == 0) srow[nr] = rowptr[r0 + nr];
+    T xrow = T(0);
+    if (FUSED && tid < nr) xrow = xs * x[r0 + tid];
     __syncthreads();
     const int p0 = srow[0], p1 = srow[nr];
     const int rs = (tid < nr) ? srow[tid] : p1, re = (tid < nr) ? srow[tid + 1] : p1;
@@ -98,8 +111,56 @@ __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* 
       for (int q = a; q < b; ++q) acc += prod[q - c0];
       __syncthreads();
     }
-    if (tid < nr) y[r0 + tid] = acc;
+    if (FUSED) acc *= xs;  // A*(xs*x) = xs*(A*x): one multiply per row instead of one per entry
+    if (tid < nr) {
+      y[r0 + tid] = acc;
+      if (FUSED) {
+        if (vj_out != nullptr) vj_out[r0 + tid] = xrow;
+        dxy += xrow * acc;
+        dyy += acc * acc;
+      }
+    }
   }
+  if (!FUSED || dots_out == nullptr) return;
+  dxy = tma::warp_sum(dxy);
+  dyy = tma::warp_sum(dyy);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = dxy; red[1][tid >> 5] = dyy; }
+  __syncthreads();
+  if (tid < 2) {
+    T sum = T(0);
+#pragma unroll
+    for (int w = 0; w < ROWS / 32; ++w) sum += red[tid][w];
+    partial[(size_t)blockIdx.x * 2 + tid] = sum;
+  }
+  tma::finish_grid_reduce(partial, 2, 2, dots_out, ticket);
+}
+
+template <typename T, bool FUSED>
+int launch_spmv_stream(cudaStream_t s, int nrows, const int* rowptr, const int* col, const T* val, const T* x, T* y,
+                       int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out, unsigned int* ticket) {
+  static const int rows_env = getenv("AB200_SPMV_ROWS") ? atoi(getenv("AB200_SPMV_ROWS")) : 256;
+  const long long cap = 148LL * 8;
+  if (rows_env == 512) {
+    constexpr int ROWS = 512, CAP = 9 * 512;
+    long long g = ((long long)nrows + ROWS - 1) / ROWS;
+    const int grid = (int)(g > cap / 2 ? cap / 2 : g);
+    k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
+                                                               partial, dots_out, ticket);
+  } else if (rows_env == 128) {
+    constexpr int ROWS = 128, CAP = 9 * 128;
+    long long g = ((long long)nrows + ROWS - 1) / ROWS;
+    const int grid = (int)(g > cap * 2 ? cap * 2 : g);
+    k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
+                                                               partial, dots_out, ticket);
+  } else {
+    constexpr int ROWS = 256, CAP = 9 * 256;
+    long long g = ((long long)nrows + ROWS - 1) / ROWS;
+    const int grid = (int)(g > cap ? cap : g);
+    k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
+                                                               partial, dots_out, ticket);
+  }
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 template <typename T>
@@ -112,15 +173,9 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   const long long nnz = nnz_hint > 0 ? nnz_hint : 0;
   ProfScope ps(s, "csr_spmv", (double)nnz * (sizeof(T) + 4.0) + (nrows + 1) * 4.0 + 2.0 * nrows * sizeof(T));
   static const bool use_stream = (getenv("AB200_SPMV") == nullptr || std::strcmp(getenv("AB200_SPMV"), "subwarp") != 0);
-  if (use_stream && avg <= 8.5) {
-    constexpr int ROWS = 256, CAP = 2304;
-    long long g = ((long long)nrows + ROWS - 1) / ROWS;
-    const long long cap = 148LL * 8;
-    const int grid = (int)(g > cap ? cap : g);
-    k_csr_spmv_stream<T, ROWS, CAP><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh);
-    launch_stats().kernels++;
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-  }
+  if (use_stream && avg <= 8.5)
+    return launch_spmv_stream<T, false>(s, nrows, rowptr, col, val, x, y, nloc, xh, T(1), nullptr, nullptr, nullptr,
+                                        nullptr);
   auto grid_for = [&](int lpr) {
     long long g = ((long long)nrows * lpr + threads - 1) / threads;
     const long long cap = 148LL * 32;
@@ -294,9 +349,36 @@ inline int gen_grid(long long n) {
 }  // namespace
 }  // namespace ab200
 
+namespace ab200 {
+// C++ entry points used by api.cu for the registered-operator mode (see driver.hpp)
+template <typename T>
+int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y) {
+  return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, 0, nullptr, op.nnz);
+}
+template <typename T>
+int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* y, T* partial, T* dots_out,
+                       unsigned int* ticket) {
+  if (op.nrows <= 0) return 0;
+  const double avg = op.nnz > 0 ? (double)op.nnz / op.nrows : 8.0;
+  if (avg > 8.5) return 1;  // caller falls back to start_step + plain SpMV
+  cudaStream_t s = cur_stream();
+  ProfScope ps(s, "csr_spmv_fused",
+               (double)op.nnz * (sizeof(T) + 4.0) + (op.nrows + 1) * 4.0 + 3.0 * op.nrows * sizeof(T));
+  return launch_spmv_stream<T, true>(s, op.nrows, op.rowptr, op.col, op.val, resid, y, 0, nullptr, inv, vj, partial,
+                                     dots_out, ticket);
+}
+template int csr_op_apply<double>(const CsrOpDesc<double>&, const double*, double*);
+template int csr_op_apply<float>(const CsrOpDesc<float>&, const float*, float*);
+template int csr_op_apply_fused<double>(const CsrOpDesc<double>&, double, const double*, double*, double*, double*,
+                                        double*, unsigned int*);
+template int csr_op_apply_fused<float>(const CsrOpDesc<float>&, float, const float*, float*, float*, float*, float*,
+                                       unsigned int*);
+}  // namespace ab200
+
 using namespace ab200;
 
 extern "C" {
+
 
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
   return launch_spmv<double>(nrows, rowptr, col, val, x, y, 0, nullptr, nnz_of(nrows, rowptr));

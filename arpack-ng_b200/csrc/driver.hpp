@@ -1,0 +1,24 @@
+// driver.hpp -- C++ view of the driver-layer operators for the solver's registered-operator mode.
+#pragma once
+namespace ab200 {
+
+// A square CSR operator resident in HBM (int32 indices), registered for a solve with ab200_register_csr_op_*.
+template <typename T>
+struct CsrOpDesc {
+  int nrows = 0;
+  long long nnz = 0;
+  const int* rowptr = nullptr;
+  const int* col = nullptr;
+  const T* val = nullptr;
+};
+
+// y = A x on the library stream
+template <typename T>
+int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y);
+// Fused K1+K2+K3: v_j = inv*resid, y = A v_j, dots_out = {v_j^T y, y^T y}; returns 1 when the operator's row
+// lengths do not suit the fused kernel (the caller then runs start_step + csr_op_apply)
+template <typename T>
+int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* y, T* partial, T* dots_out,
+                       unsigned int* ticket);
+
+}  // namespace ab200

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "hostmath.hpp"
@@ -64,6 +65,13 @@ class IrlBase {
 
   Counters cnt;
   const Counters& counters() const { return cnt; }
+  // largest relative disagreement between the SpMV-epilogue dots and the CGS sweep (registered-operator mode)
+  T fused_dot_maxdiff = 0;
+  void set_registered_op(std::function<void(const T*, T*)> op,
+                         std::function<bool(T, const T*, T*, T*, T*)> fused) {
+    op_ = std::move(op);
+    fused_op_ = std::move(fused);
+  }
 
   // *eupd on a context that never ran *aupd (fresh process): make sure the mailbox exists
   void ensure_mailbox(int ncv) {
@@ -102,6 +110,12 @@ class IrlBase {
   T* hC() { return mbh_.data() + 2 * seg_; }
 
   SeedState* seed_ = nullptr;
+
+  // registered operator (opt-in extension, mode 1 / bmat='I'): the solver applies OP itself instead of
+  // returning ido = +-1, so a whole solve is one *aupd call (the arpackmm-style driver loop, natively)
+  std::function<void(const T* x, T* y)> op_;
+  std::function<bool(T inv, const T* resid, T* vj, T* y, T* mb_dots)> fused_op_;
+  bool ai_fused_op_ = false;
 
   T* vcol(int j1) { return v_ + (int64_t)(j1 - 1) * ldv_; }  // 1-based column
   T* slot(int off1) { return workd_ + (off1 - 1); }           // 1-based workd offset
@@ -147,9 +161,13 @@ class IrlBase {
     if ((!par_ && gv_itry_ == 1) || (par_ && bmat_ == 'G')) {
       cnt.nopx++;
       ops_->copy(n_, resid_, slot(1));
-      ipntr_[0] = 1; ipntr_[1] = n_ + 1;
-      ido_ = -1;
-      CO_YIELD(gv_pc_);
+      if (op_ && mode_ == 1) {
+        op_(slot(1), slot(n_ + 1));
+      } else {
+        ipntr_[0] = 1; ipntr_[1] = n_ + 1;
+        ido_ = -1;
+        CO_YIELD(gv_pc_);
+      }
       ops_->copy(n_, slot(n_ + 1), resid_);
     } else if (!par_ && gv_itry_ > 1 && bmat_ == 'G') {
       ops_->copy(n_, resid_, slot(n_ + 1));
@@ -240,7 +258,12 @@ class IrlBase {
         }
       }
       // v_j = r/||r||, p_j = B r/||r||, x = v_j   (dsaitr.f:438-468)
-      {
+      ai_fused_op_ = false;
+      if (fused_op_ && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm()) {
+        // registered operator: K1+K2+K3 in one kernel (v_j written on the way, x never materialised)
+        ai_fused_op_ = fused_op_(T(1) / rnorm_, resid_, vcol(ai_j_), slot(irj()), mbC() + 2);
+      }
+      if (!ai_fused_op_) {
         const T tiny = tiny_norm();
         if (rnorm_ >= tiny) {
           ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(ai_j_), slot(ivj()), slot(IPJ), bmat_ == 'I');
@@ -255,14 +278,25 @@ class IrlBase {
         }
       }
       cnt.nopx++;
-      ipntr_[0] = ivj(); ipntr_[1] = irj(); ipntr_[2] = IPJ;
-      ido_ = 1;
-      CO_YIELD(ai_pc_);
+      if (op_ && mode_ == 1) {
+        if (!ai_fused_op_) op_(slot(ivj()), slot(irj()));  // registered operator: no hand-off
+      } else {
+        ipntr_[0] = ivj(); ipntr_[1] = irj(); ipntr_[2] = IPJ;
+        ido_ = 1;
+        CO_YIELD(ai_pc_);
+      }
       // workd(irj) = OP*v_j
       if (bmat_ == 'I' && mode_ != 2) {
         // ---- fused path: CGS + speculative DGKS, one host round trip (K4..K10) ----
         ops_->orth_step(n_, ai_j_, v_, ldv_, slot(irj()), resid_, mbA(), mbB(), mbC());
-        ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 2);
+        ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
+        if (ai_fused_op_) {
+          // alpha = v_j^T OP v_j and ||OP v_j||^2 from the SpMV epilogue must agree with the CGS sweep
+          const T da = std::fabs(hC()[2] - hA()[ai_j_ - 1]), dw = std::fabs(hC()[3] - hA()[ai_j_]);
+          const T sc = std::sqrt(hA()[ai_j_]);
+          fused_dot_maxdiff = std::max(fused_dot_maxdiff, std::max(da / (sc > T(0) ? sc : T(1)),
+                                                                   dw / (hA()[ai_j_] > T(0) ? hA()[ai_j_] : T(1))));
+        }
         ai_wnorm_ = std::sqrt(hA()[ai_j_]);
         h_store(ai_j_, hA(), ai_beta_, ai_rstart_);
         rnorm_ = std::sqrt(hB()[ai_j_]);

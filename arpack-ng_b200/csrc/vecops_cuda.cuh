@@ -123,6 +123,12 @@ class CudaVecOps final : public VecOps<T> {
   void set_stream(cudaStream_t s) { stream_ = s; }
   // 0 = auto (TMA-tiled kernels when the layout allows), 1 = force the generic kernels
   void set_kernel_mode(int m) { kernel_mode_ = m; }
+  // scratch of the deterministic two-stage reductions, shared with driver-layer kernels that run on the same stream
+  T* reduction_scratch(size_t count) {
+    ensure_partial(count);
+    return partial_;
+  }
+  unsigned int* reduction_ticket() { return ticket_; }
 
  private:
   cudaStream_t stream_;

@@ -133,6 +133,15 @@ void ab200_release_all(void);
 void ab200_launch_stats(unsigned long long* out4);
 /* forget the SAVE'd dgetv0 seed / dnaitr smlnum, as if the process had just started */
 void ab200_reset_seed(void);
+/* Registered-operator mode (opt-in; strict RCI stays the default): the library applies y = A x (square CSR matrix in
+ * HBM, int32 indices) itself for the solve keyed to `workl` (mode 1, bmat 'I'), so one *aupd_c call runs the whole solve
+ * -- the loop of EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:787-846 without a host round trip per step.  K1+K2 are folded
+ * into the SpMV and alpha = v^T OP v, ||OP v||^2 come out of its epilogue.  nrows = 0 unregisters. */
+int ab200_register_csr_op_f64(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
+                              const double* val);
+int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
+                              const float* val);
+double ab200_fused_dot_maxdiff(const void* workl);
 /* per-kernel CUDA-event timing on the launching stream (bench.py's roofline): enable, run, read the table */
 void ab200_profile_enable(int on);
 void ab200_profile_reset(void);

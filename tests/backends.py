@@ -225,6 +225,9 @@ def hostdouble_lib():
         L.hd_free.argtypes = [C.c_void_p, C.c_int]
         L.hd_set_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ALLREDUCE_FN]
         L.hd_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p]
+        L.hd_set_registered_op.argtypes = [C.c_void_p, C.c_int, OP_FN, C.c_int, C.c_int]
+        L.hd_fused_dot_maxdiff.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hd_fused_dot_maxdiff.restype = C.c_double
         for p, rp, rt in (("d", c_dbl_p, C.c_double), ("s", c_flt_p, C.c_float)):
             for fam in ("s", "n"):
                 f = getattr(L, f"hd_{p}{fam}aupd")
@@ -242,6 +245,9 @@ def hostdouble_lib():
             f.restype = None
         _hd = L
     return _hd
+
+
+OP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
 
 
 class HostDouble(Oracle):
@@ -266,6 +272,23 @@ class HostDouble(Oracle):
 
     def _ctxargs(self, p):
         return (self._procs[p == "d"],)
+
+    def register_op(self, op, n, dtype=np.float64, fused=False):
+        """Registered-operator mode of the product's control code: OP is applied inside *aupd (no ido=+-1)."""
+        dt = np.dtype(dtype)
+        isd = dt == np.float64
+
+        def cb(xp, yp, nn):
+            ct = C.c_double if isd else C.c_float
+            x = np.ctypeslib.as_array(C.cast(xp, C.POINTER(ct)), shape=(nn,))
+            y = np.ctypeslib.as_array(C.cast(yp, C.POINTER(ct)), shape=(nn,))
+            y[:] = op(x.copy())
+        self._opcb = OP_FN(cb) if op is not None else C.cast(None, OP_FN)
+        self.L.hd_set_registered_op(self._procs[isd], int(isd), self._opcb, n, int(fused))
+
+    def fused_dot_maxdiff(self, sym=True, dtype=np.float64):
+        isd = np.dtype(dtype) == np.float64
+        return self.L.hd_fused_dot_maxdiff(self._procs[isd], int(isd), int(sym))
 
     def stats(self, sym=True, dtype=np.float64):
         out = np.zeros(5, dtype=np.int32)

@@ -26,6 +26,7 @@ namespace {
 using namespace ab200;
 
 typedef void (*allreduce_fn)(void* user, void* buf, int count, int is_double, int op);
+typedef void (*op_fn)(const void* x, void* y, int n);
 
 template <typename T>
 struct HostVecOps final : VecOps<T> {
@@ -182,6 +183,32 @@ struct Proc {  // one "process": SAVE'd seed etc.
   bool par = false;
   std::unique_ptr<IrlSym<T>> sym;
   std::unique_ptr<IrlNonsym<T>> nonsym;
+  // registered-operator mode (IrlBase::set_registered_op): y = OP x through a C callback, no ido = +-1 hand-offs
+  op_fn reg_op = nullptr;
+  int reg_fused = 0;
+  int reg_n = 0;
+
+  template <typename Solver>
+  void attach(Solver* s) {
+    if (!reg_op) return;
+    op_fn f = reg_op;
+    const int n = reg_n;
+    auto plain = [f, n](const T* x, T* y) { f((const void*)x, (void*)y, n); };
+    if (!reg_fused) {
+      s->set_registered_op(plain, nullptr);
+      return;
+    }
+    // host emulation of the fused SpMV: vj = inv*resid, y = OP vj, dots {vj.y, y.y}
+    s->set_registered_op(plain, [f, n](T inv, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+      for (int i = 0; i < n; ++i) vj[i] = inv * resid[i];
+      f((const void*)vj, (void*)y, n);
+      T a = 0, b = 0;
+      for (int i = 0; i < n; ++i) { a += vj[i] * y[i]; b += y[i] * y[i]; }
+      mb_dots[0] = a;
+      mb_dots[1] = b;
+      return true;
+    });
+  }
 };
 
 }  // namespace
@@ -197,6 +224,15 @@ void hd_set_comm(void* p, int is_double, int rank, int nranks, allreduce_fn fn) 
   if (is_double) { auto* q = (Proc<double>*)p; q->par = true; q->ops.rank_ = rank; q->ops.nranks_ = nranks; q->ops.ar_ = fn; }
   else { auto* q = (Proc<float>*)p; q->par = true; q->ops.rank_ = rank; q->ops.nranks_ = nranks; q->ops.ar_ = fn; }
 }
+void hd_set_registered_op(void* p, int is_double, op_fn fn, int n, int fused) {
+  if (is_double) { auto* q = (Proc<double>*)p; q->reg_op = fn; q->reg_n = n; q->reg_fused = fused; }
+  else { auto* q = (Proc<float>*)p; q->reg_op = fn; q->reg_n = n; q->reg_fused = fused; }
+}
+double hd_fused_dot_maxdiff(void* p, int is_double, int fam_sym) {
+  if (is_double) { auto* q = (Proc<double>*)p; return fam_sym ? q->sym->fused_dot_maxdiff : q->nonsym->fused_dot_maxdiff; }
+  auto* q = (Proc<float>*)p;
+  return fam_sym ? q->sym->fused_dot_maxdiff : q->nonsym->fused_dot_maxdiff;
+}
 void hd_stats(void* p, int is_double, int fam_sym, int* out5) {
   const Counters* c = nullptr;
   if (is_double) { auto* q = (Proc<double>*)p; c = fam_sym ? &q->sym->counters() : &q->nonsym->counters(); }
@@ -211,6 +247,8 @@ void hd_stats(void* p, int is_double, int fam_sym, int* out5) {
     if (*ido == 0) {                                                                                             \
       if (ISSYM) q->sym.reset(new IrlSym<T>(&q->ops, q->par, &q->seed));                                         \
       else q->nonsym.reset(new IrlNonsym<T>(&q->ops, q->par, &q->seed, &q->smlnum_first));                       \
+      if (ISSYM) q->attach(q->sym.get());                                                                        \
+      else q->attach(q->nonsym.get());                                                                           \
     }                                                                                                            \
     if (ISSYM) q->sym->aupd(ido, bmat[0], n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl,   \
                             lworkl, info);                                                                       \

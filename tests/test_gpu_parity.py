@@ -248,3 +248,55 @@ def test_laplace3d_generator_and_spmv(ab):
 def test_kernels_counted(ab):
     st = ab.launch_stats()
     assert st["kernels"] > 0
+
+
+# --------------------------------------------------------------------------------------------------
+# registered-operator mode: OP applied by the library, K1+K2+K3 fused
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["lap2d_small", "lap2d_tma", "lap3d", "convdiff", "lap2d_f32"])
+def test_registered_csr_operator_matches_rci_and_oracle(ab, case):
+    torch = _torch()
+    sym, dtype, rtol = True, np.float64, RTOL64
+    if case == "lap2d_small":
+        A, nev, ncv, which = ab.CsrOperator.laplace2d(37, 29), 4, 16, "LA"
+    elif case == "lap2d_tma":
+        A, nev, ncv, which = ab.CsrOperator.laplace2d(300, 260), 6, 24, "LA"
+    elif case == "lap3d":
+        A, nev, ncv, which = ab.CsrOperator.laplace3d(24, 20, 22), 5, 20, "LA"
+    elif case == "convdiff":
+        A, nev, ncv, which, sym = ab.CsrOperator.convdiff2d(40, rho=10.0), 4, 20, "LM", False
+    else:
+        A, nev, ncv, which, dtype, rtol = ab.CsrOperator.laplace2d(64, 48), 4, 16, "LA", np.float32, RTOL32
+        A = ab.CsrOperator(A.n, A.rowptr, A.col, A.val.float())
+    n = A.n
+    r0 = np.random.default_rng(5).uniform(-1, 1, n)
+    tol = 1e-10 if dtype == np.float64 else 1e-5
+    a = ab.solve(A, n, nev, ncv, which, sym=sym, tol=tol, mxiter=3000, resid=r0, dtype=dtype)
+    b = ab.solve(None, n, nev, ncv, which, sym=sym, tol=tol, mxiter=3000, resid=r0, dtype=dtype, registered_op=A)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert b.nsteps == 0 and a.nsteps > 0          # the whole solve ran inside one *aupd_c call
+    assert _counts(a) == _counts(b)
+    if sym:
+        assert np.abs(a.d - b.d).max() <= rtol * np.abs(a.d).max()
+    else:
+        assert np.abs(a.dr - b.dr).max() <= rtol * np.abs(a.dr).max()
+        assert np.abs(a.di - b.di).max() <= rtol * max(np.abs(a.dr).max(), 1e-300)
+    # the SpMV-epilogue dots (alpha, ||OP v||^2) agree with the CGS sweep of the same step
+    assert b.fused_dot_maxdiff is not None and 0.0 <= b.fused_dot_maxdiff < (1e-11 if dtype == np.float64 else 1e-3)
+    # and against the CPU oracle on the same start vector
+    S = A.to_scipy().astype(dtype)
+    ref = Oracle().solve(lambda x: S @ x, n, nev, ncv, which, sym=sym, tol=tol, mxiter=3000, resid=r0, dtype=dtype,
+                         c_abi_tol=True)
+    assert ref.info == 0
+    if dtype == np.float64:
+        assert _counts(b) == _counts(ref)
+    if sym:
+        assert np.abs(b.d - ref.d).max() <= rtol * np.abs(ref.d).max()
+    else:
+        assert np.abs(np.sort(b.dr[:nev]) - np.sort(ref.dr[:nev])).max() <= rtol * np.abs(ref.dr).max()
+
+
+def test_registered_operator_row_count_mismatch_fails_loudly(ab):
+    A = ab.CsrOperator.laplace2d(20, 20)
+    r = ab.solve(None, A.n - 1, 3, 12, "LA", tol=1e-8, mxiter=10, registered_op=A, eupd=False)
+    assert r.info == -9990

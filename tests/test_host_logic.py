@@ -308,3 +308,45 @@ def test_parpack_nonsym_semantics_match_oracle():
         assert ra.info == rb.info == 0
         assert counts(ra) == counts(rb)
         assert np.abs(ra.dr - rb.dr).max() / np.abs(rb.dr).max() < 1e-10
+
+
+@pytest.mark.parametrize("sym,fused", [(True, False), (True, True), (False, False), (False, True)])
+def test_registered_operator_runs_whole_solve_in_one_call(sym, fused):
+    """§8(f) row 2: with a registered OP the solve never hands off (no ido=+-1) and gives the RCI result bit for bit
+    (the control flow is the same code; only the yield is replaced by the operator call)."""
+    nx = 14
+    if sym:
+        A, nev, ncv, which = laplace2d(nx, nx + 3), 4, 16, "LA"
+    else:
+        A, nev, ncv, which = convdiff2d(nx, rho=10.0), 4, 16, "LM"
+    n = A.shape[0]
+    r0 = start(n, 11)
+    op = lambda x: A @ x
+    a = HostDouble().solve(op, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
+    hd = HostDouble()
+    hd.register_op(op, n, fused=fused)
+    b = hd.solve(None, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert b.nsteps == 0 and a.nsteps > 0            # one *aupd call, no hand-off
+    assert a.stats == b.stats and counts(a) == counts(b)
+    assert np.array_equal(a.v, b.v) and np.array_equal(a.workl, b.workl)
+    if sym:
+        assert np.array_equal(a.d, b.d)
+    else:
+        assert np.array_equal(a.dr, b.dr) and np.array_equal(a.di, b.di)
+    if fused:
+        assert 0.0 <= hd.fused_dot_maxdiff(sym) < 1e-12
+
+
+def test_registered_operator_is_ignored_outside_mode1():
+    """The registration applies to mode 1 / bmat='I' only; shift-invert keeps the RCI hand-offs."""
+    import scipy.sparse.linalg as spla
+    nx = 12
+    A = laplace2d(nx, nx)
+    n = A.shape[0]
+    lu = spla.splu(A.tocsc())
+    hd = HostDouble()
+    hd.register_op(lambda x: A @ x, n, fused=True)
+    r = hd.solve(lambda x: lu.solve(x), n, 4, 12, "LM", tol=1e-10, mxiter=300, mode=3, sigma=0.0, resid=start(n))
+    assert r.info == 0 and r.nsteps > 0
+    assert np.allclose(np.sort(r.d), np.sort(np.linalg.eigvalsh(A.toarray()))[:4], rtol=1e-9)
