@@ -226,9 +226,28 @@ class Result(dict):
     __getattr__ = dict.__getitem__
 
 
+def alloc_host_buffers(n, ncv, dtype=np.float64, pinned=True):
+    """(V, workd, resid) as host tensors of the sizes a reference caller declares; pinned by default."""
+    import torch
+    t_dt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+
+    def _h(cnt):
+        t = torch.zeros(cnt, dtype=t_dt)
+        return t.pin_memory() if pinned else t
+    return _h(n * ncv), _h(3 * n), _h(n)
+
+
+def alloc_device_buffers(n, ncv, dtype=np.float64, device="cuda"):
+    """(V, workd, resid) in HBM, the device-resident twin of alloc_host_buffers."""
+    import torch
+    t_dt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    return (torch.zeros(n * ncv, dtype=t_dt, device=device), torch.zeros(3 * n, dtype=t_dt, device=device),
+            torch.zeros(n, dtype=t_dt, device=device))
+
+
 def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.float64,
           bop=None, rvec=True, sigma=0.0, sigmai=0.0, device="cuda", host_buffers=False, comm=None, ishift=1,
-          eupd=True, pinned=True, registered_op=None):
+          eupd=True, pinned=True, registered_op=None, buffers=None):
     """Run a whole *aupd/*eupd solve through the C-ABI.
 
     device arrays (default): resid/v/workd are torch CUDA tensors; ``op(x, y)`` receives tensor views of the
@@ -249,22 +268,22 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
     info = np.zeros(1, dtype=np.int32)
     ldv = n
     if host_buffers:
-        def _h(cnt):
-            t = torch.zeros(cnt, dtype=t_dt)
-            return t.pin_memory() if pinned else t
-        v_t, workd_t, resid_t = _h(ldv * ncv), _h(3 * n), _h(n)
+        # the caller's own arrays, as dssimp.f:213-219 declares them; reusable across solves via `buffers`
+        v_t, workd_t, resid_t = buffers if buffers is not None else alloc_host_buffers(n, ncv, np_dt, pinned)
         v, workd, res = v_t.numpy(), workd_t.numpy(), resid_t.numpy()
         if resid is not None:
             res[:] = np.asarray(resid, dtype=np_dt)
             info[0] = 1
-    else:
-        v = torch.zeros(ldv * ncv, dtype=t_dt, device=device)
-        workd = torch.zeros(3 * n, dtype=t_dt, device=device)
+    elif buffers is not None:
+        v, workd, res = buffers          # the caller's device arrays, reused across solves
         if resid is not None:
-            res = torch.as_tensor(resid, dtype=t_dt).to(device).contiguous().clone()
+            res.copy_(torch.as_tensor(resid, dtype=t_dt))
             info[0] = 1
-        else:
-            res = torch.zeros(n, dtype=t_dt, device=device)
+    else:
+        v, workd, res = alloc_device_buffers(n, ncv, np_dt, device)
+        if resid is not None:
+            res.copy_(torch.as_tensor(resid, dtype=t_dt))
+            info[0] = 1
     if registered_op is not None:
         # opt-in extension: the library applies the CSR operator itself (one *aupd call per solve)
         if registered_op.val.dtype != t_dt:

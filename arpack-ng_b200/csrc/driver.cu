@@ -7,6 +7,7 @@
 // operator generators for BASELINE.json's configs, the hashed start vector, and the residual check.
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,18 @@ void nccl_halo_exchange(NcclComm* c, const void* send_lo, void* recv_lo, size_t 
 namespace {
 
 inline cudaStream_t cur_stream() { return (cudaStream_t)ab200_get_stream(); }
+
+// SpMV kernel choice for short-row matrices: 0 = CSR-bulk (default), 1 = CSR-stream, 2 = row per sub-warp.
+// Initialised from AB200_SPMV={bulk,stream,subwarp}; ab200_set_spmv_variant() overrides it (tests, tuning).
+int& spmv_variant() {
+  static int v = [] {
+    const char* e = getenv("AB200_SPMV");
+    if (e && std::strcmp(e, "stream") == 0) return 1;
+    if (e && std::strcmp(e, "subwarp") == 0) return 2;
+    return 0;
+  }();
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // CSR SpMV, LPR lanes per row (power of two <= 32).  Rows of the target operators are short
@@ -135,6 +148,278 @@ __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* 
   tma::finish_grid_reduce(partial, 2, 2, dots_out, ticket);
 }
 
+// "CSR-bulk" variant: the same row-block scheme fed by the copy engine.  A persistent CTA walks row blocks of ROWS
+// rows; one producer thread streams each block's slice of the col/val arrays (contiguous in CSR) and its ROWS+1 row
+// pointers into a shared-memory ring with cp.async.bulk (1-D bulk copies, 16-byte granules, mbarrier complete_tx), so the
+// DRAM streams stay in flight while the ROWS consumer threads are busy with the x gathers of earlier blocks.  The
+// consumers are software-pipelined one block deep: the x gathers of block b+1 are issued (into registers) before the
+// barrier / row sums / y store of block b.  Products are parked in the staged val slice, consumers synchronise among
+// themselves (named barrier; the producer warp never joins) and every thread sums its own row in entry order -- the
+// row sums are bit-identical to the CSR-stream kernel's.
+// Bulk copies need 16-byte aligned sources: a block's slice starts at its first entry rounded down to a multiple of
+// 4 entries (the pad entries belong to the previous block and are ignored) and never extends past nnz & ~3; the <= 3
+// tail entries of the matrix are read directly.  A block with more than CAP entries is not staged: its consumers
+// stream it from global memory chunk by chunk (the CSR-stream scheme) with the slot's val array as scratch.
+template <typename T, int ROWS, int CAP>
+struct SpmvBulkStage {
+  T val[CAP + 4];
+  int col[CAP + 4];
+  int rp[ROWS + 4];
+};
+
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(tma::smem_u32(bar))
+               : "memory");
+}
+
+template <typename T, int ROWS, int CAP, int NST, bool FUSED>
+__global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const int* __restrict__ rowptr,
+                                                             const int* __restrict__ col, const T* __restrict__ val,
+                                                             const T* __restrict__ x, T* __restrict__ y, int nloc,
+                                                             const T* __restrict__ xh, T xs, T* __restrict__ vj_out,
+                                                             T* __restrict__ partial, T* __restrict__ dots_out,
+                                                             unsigned int* ticket) {
+  using Stage = SpmvBulkStage<T, ROWS, CAP>;
+  constexpr int EPT = CAP / ROWS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Stage* stages = reinterpret_cast<Stage*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * NST);
+  uint64_t* empty = full + NST;
+  __shared__ T red[2][ROWS / 32];
+  const int tid = threadIdx.x;
+  const int nblk = (nrows + ROWS - 1) / ROWS;
+  const int gstep = (int)gridDim.x;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      tma::mbar_init(&full[i], 1);
+      tma::mbar_init(&empty[i], ROWS / 32);
+    }
+    tma::mbar_fence_init();
+  }
+  __syncthreads();
+  const int nnz4 = __ldg(rowptr + nrows) & ~3;
+  T dxy = T(0), dyy = T(0);
+  if (tid >= ROWS) {
+    // ---------------- producer warp ----------------
+    const int lane = tid - ROWS;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int base = blockIdx.x; base < nblk; base += 32 * gstep) {
+      // row-pointer bounds of the next 32 blocks of this CTA, one per lane (one load latency per 32 blocks)
+      const int myblk = base + lane * gstep;
+      int q0 = 0, q1 = 0;
+      if (myblk < nblk) {
+        const int r0 = myblk * ROWS;
+        q0 = __ldg(rowptr + r0);
+        q1 = __ldg(rowptr + ((nrows - r0 > ROWS) ? r0 + ROWS : nrows));
+      }
+      for (int l = 0; l < 32; ++l) {
+        const int blk = base + l * gstep;
+        if (blk >= nblk) break;
+        const int p0 = __shfl_sync(0xffffffffu, q0, l), p1 = __shfl_sync(0xffffffffu, q1, l);
+        if (lane == 0) {
+          const int r0 = blk * ROWS;
+          const bool rp_bulk = (nrows + 1 - r0 >= ROWS + 4);
+          const int sidx = p0 & ~3;
+          int ce = (p1 + 3) & ~3;
+          if (ce > nnz4) ce = nnz4;
+          int cnt = ce > sidx ? ce - sidx : 0;
+          if (p1 - sidx > CAP) cnt = 0;  // oversized block: consumers stream it themselves
+          tma::mbar_wait(&empty[stage], phase ^ 1u);
+          Stage* st = &stages[stage];
+          const uint32_t bytes = (uint32_t)cnt * (uint32_t)(sizeof(T) + 4) + (rp_bulk ? (ROWS + 4) * 4u : 0u);
+          if (bytes) {
+            tma::mbar_expect_tx(&full[stage], bytes);
+            if (cnt) {
+              bulk_load(tma::smem_u32(st->val), val + sidx, (uint32_t)cnt * (uint32_t)sizeof(T), &full[stage]);
+              bulk_load(tma::smem_u32(st->col), col + sidx, (uint32_t)cnt * 4u, &full[stage]);
+            }
+            if (rp_bulk) bulk_load(tma::smem_u32(st->rp), rowptr + r0, (ROWS + 4) * 4u, &full[stage]);
+          } else {
+            tma::mbar_arrive(&full[stage]);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers: thread t owns row r0 + t ----------------
+    // registers of one block: its entries' columns, values and gathered x, and the owner row's bounds
+    struct Item {
+      int cc[EPT];
+      T vv[EPT], xx[EPT];
+      int rs, re, sidx, p1;
+      T xrow;
+      bool direct;
+    };
+    auto load_item = [&](Item& it, int blk, Stage* st) {
+      const int r0 = blk * ROWS;
+      const int nr = (nrows - r0 < ROWS) ? (nrows - r0) : ROWS;
+      int p0;
+      if (nrows + 1 - r0 >= ROWS + 4) {
+        p0 = st->rp[0];
+        it.p1 = st->rp[ROWS];
+        it.rs = st->rp[tid];
+        it.re = st->rp[tid + 1];
+      } else {
+        p0 = __ldg(rowptr + r0);
+        it.p1 = __ldg(rowptr + r0 + nr);
+        it.rs = (tid < nr) ? __ldg(rowptr + r0 + tid) : it.p1;
+        it.re = (tid < nr) ? __ldg(rowptr + r0 + tid + 1) : it.p1;
+      }
+      it.xrow = T(0);
+      if (FUSED && tid < nr) it.xrow = xs * x[r0 + tid];
+      it.sidx = p0 & ~3;
+      const int len = it.p1 - it.sidx;
+      it.direct = len > CAP;
+      if (it.direct) return;
+      int clen = ((it.p1 + 3) & ~3);
+      clen = (clen > nnz4 ? nnz4 : clen) - it.sidx;
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int i = tid + k * ROWS;
+        it.cc[k] = 0;
+        it.vv[k] = T(0);
+        if (i < clen) { it.cc[k] = st->col[i]; it.vv[k] = st->val[i]; }
+        else if (i < len) { it.cc[k] = __ldg(col + it.sidx + i); it.vv[k] = __ldg(val + it.sidx + i); }
+      }
+#pragma unroll
+      for (int k = 0; k < EPT; ++k)
+        it.xx[k] = (xh != nullptr && it.cc[k] >= nloc) ? xh[it.cc[k] - nloc] : x[it.cc[k]];
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    int blk = blockIdx.x;
+    Item cur, nxt;
+    if (blk < nblk) {
+      tma::mbar_wait(&full[0], 0u);
+      load_item(cur, blk, &stages[0]);
+    }
+    while (blk < nblk) {
+      Stage* st = &stages[stage];
+      const int r0 = blk * ROWS;
+      const int nr = (nrows - r0 < ROWS) ? (nrows - r0) : ROWS;
+      T acc = T(0);
+      if (!cur.direct) {
+        const int len = cur.p1 - cur.sidx;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          const int i = tid + k * ROWS;
+          if (i < len) st->val[i] = cur.vv[k] * cur.xx[k];
+        }
+      } else {
+        // oversized block, streamed from global memory in chunks of CAP entries
+        for (int c0 = cur.sidx; c0 < cur.p1; c0 += CAP) {
+          const int c1 = (cur.p1 - c0 > CAP) ? c0 + CAP : cur.p1;
+          for (int i = c0 + tid; i < c1; i += ROWS) {
+            const int c = __ldg(col + i);
+            const T xv = (xh != nullptr && c >= nloc) ? xh[c - nloc] : x[c];
+            st->val[i - c0] = __ldg(val + i) * xv;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(ROWS) : "memory");
+          const int a = (cur.rs > c0) ? cur.rs : c0, b = (cur.re < c1) ? cur.re : c1;
+          for (int q = a; q < b; ++q) acc += st->val[q - c0];
+          asm volatile("bar.sync 1, %0;" ::"n"(ROWS) : "memory");
+        }
+      }
+      // the next block's gathers go out before this block's barrier and row sums
+      const int nblk_next = blk + gstep;
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == NST) { nstage = 0; nphase ^= 1u; }
+      if (nblk_next < nblk) {
+        tma::mbar_wait(&full[nstage], nphase);
+        load_item(nxt, nblk_next, &stages[nstage]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(ROWS) : "memory");
+      if (!cur.direct)
+        for (int q = cur.rs; q < cur.re; ++q) acc += st->val[q - cur.sidx];
+      __syncwarp();
+      if ((tid & 31) == 0) tma::mbar_arrive(&empty[stage]);
+      if (FUSED) acc *= xs;  // A*(xs*x) = xs*(A*x): one multiply per row instead of one per entry
+      if (tid < nr) {
+        y[r0 + tid] = acc;
+        if (FUSED) {
+          if (vj_out != nullptr) vj_out[r0 + tid] = cur.xrow;
+          dxy += cur.xrow * acc;
+          dyy += acc * acc;
+        }
+      }
+      cur = nxt;
+      stage = nstage;
+      phase = nphase;
+      blk = nblk_next;
+    }
+  }
+  if (!FUSED || dots_out == nullptr) return;
+  if (tid < ROWS) {
+    dxy = tma::warp_sum(dxy);
+    dyy = tma::warp_sum(dyy);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = dxy; red[1][tid >> 5] = dyy; }
+  }
+  __syncthreads();
+  if (tid < 2) {
+    T sum = T(0);
+#pragma unroll
+    for (int w = 0; w < ROWS / 32; ++w) sum += red[tid][w];
+    partial[(size_t)blockIdx.x * 2 + tid] = sum;
+  }
+  tma::finish_grid_reduce(partial, 2, 2, dots_out, ticket);
+}
+
+template <typename T, int ROWS, int CAP, int NST, bool FUSED>
+int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long nnz, const int* rowptr, const int* col,
+                         const T* val, const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial,
+                         T* dots_out, unsigned int* ticket) {
+  using Stage = SpmvBulkStage<T, ROWS, CAP>;
+  constexpr size_t smem = sizeof(Stage) * NST + 2 * NST * sizeof(uint64_t);
+  auto kern = k_csr_spmv_bulk<T, ROWS, CAP, NST, FUSED>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    attr_done = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long nblk = ((long long)nrows + ROWS - 1) / ROWS;
+  long long g = (long long)sms * ctas_per_sm;
+  if (g > nblk) g = nblk;
+  (void)nnz;
+  kern<<<(int)g, ROWS + 32, smem, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out, partial, dots_out, ticket);
+  launch_stats().kernels++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// the bulk kernel needs 16-byte aligned CSR arrays (cp.async.bulk) and the true nnz
+inline bool spmv_bulk_ok(const int* rowptr, const int* col, const void* val, long long nnz) {
+  return spmv_variant() == 0 && nnz > 0 && (((uintptr_t)rowptr | (uintptr_t)col | (uintptr_t)val) & 15u) == 0;
+}
+
+template <typename T, bool FUSED>
+int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr, const int* col, const T* val,
+                     const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out,
+                     unsigned int* ticket) {
+  static const int variant = getenv("AB200_SPMV_BULK") ? atoi(getenv("AB200_SPMV_BULK")) : 0;
+#define AB200_BULK_CFG(ROWS_, NST_, CTAS_)                                                                         \
+  return launch_spmv_bulk_cfg<T, ROWS_, ROWS_ * 7, NST_, FUSED>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, xh, \
+                                                                xs, vj_out, partial, dots_out, ticket)
+  switch (variant) {
+    case 1: AB200_BULK_CFG(128, 3, 6);
+    case 2: AB200_BULK_CFG(256, 2, 4);
+    case 3: AB200_BULK_CFG(256, 4, 2);
+    case 4: AB200_BULK_CFG(512, 2, 2);
+    case 5: AB200_BULK_CFG(128, 2, 8);
+    default: AB200_BULK_CFG(256, 3, 3);
+  }
+#undef AB200_BULK_CFG
+}
+
 template <typename T, bool FUSED>
 int launch_spmv_stream(cudaStream_t s, int nrows, const int* rowptr, const int* col, const T* val, const T* x, T* y,
                        int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out, unsigned int* ticket) {
@@ -172,7 +457,10 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   cudaStream_t s = cur_stream();
   const long long nnz = nnz_hint > 0 ? nnz_hint : 0;
   ProfScope ps(s, "csr_spmv", (double)nnz * (sizeof(T) + 4.0) + (nrows + 1) * 4.0 + 2.0 * nrows * sizeof(T));
-  static const bool use_stream = (getenv("AB200_SPMV") == nullptr || std::strcmp(getenv("AB200_SPMV"), "subwarp") != 0);
+  const bool use_stream = spmv_variant() != 2;
+  if (use_stream && avg <= 8.5 && spmv_bulk_ok(rowptr, col, val, nnz))
+    return launch_spmv_bulk<T, false>(s, nrows, nnz, rowptr, col, val, x, y, nloc, xh, T(1), nullptr, nullptr, nullptr,
+                                      nullptr);
   if (use_stream && avg <= 8.5)
     return launch_spmv_stream<T, false>(s, nrows, rowptr, col, val, x, y, nloc, xh, T(1), nullptr, nullptr, nullptr,
                                         nullptr);
@@ -364,6 +652,9 @@ int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* 
   cudaStream_t s = cur_stream();
   ProfScope ps(s, "csr_spmv_fused",
                (double)op.nnz * (sizeof(T) + 4.0) + (op.nrows + 1) * 4.0 + 3.0 * op.nrows * sizeof(T));
+  if (spmv_bulk_ok(op.rowptr, op.col, op.val, op.nnz))
+    return launch_spmv_bulk<T, true>(s, op.nrows, op.nnz, op.rowptr, op.col, op.val, resid, y, 0, nullptr, inv, vj,
+                                     partial, dots_out, ticket);
   return launch_spmv_stream<T, true>(s, op.nrows, op.rowptr, op.col, op.val, resid, y, 0, nullptr, inv, vj, partial,
                                      dots_out, ticket);
 }
@@ -379,6 +670,8 @@ using namespace ab200;
 
 extern "C" {
 
+
+void ab200_set_spmv_variant(int variant) { spmv_variant() = (variant >= 0 && variant <= 2) ? variant : 0; }
 
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
   return launch_spmv<double>(nrows, rowptr, col, val, x, y, 0, nullptr, nnz_of(nrows, rowptr));

@@ -168,6 +168,8 @@ int ab200_comm_size(int handle);
  * does these products with Eigen on the CPU).  All pointers are DEVICE pointers unless named *_host. ---- */
 /* y = A x, CSR with int32 indices (K3 of SURVEY.md §2.3) */
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y);
+/* SpMV kernel for short-row matrices: 0 = CSR-bulk (cp.async.bulk ring, default), 1 = CSR-stream, 2 = row per sub-warp */
+void ab200_set_spmv_variant(int variant);
 int ab200_csr_spmv_f32(int nrows, const int* rowptr, const int* col, const float* val, const float* x, float* y);
 /* as above with host vectors: H2D(x), SpMV, D2H(y) -- the OP of an unmodified host RCI loop */
 int ab200_csr_spmv_hostvec_f64(int nrows, int ncols, const int* rowptr, const int* col, const double* val,

@@ -123,3 +123,95 @@ def test_reductions_are_bit_reproducible(ab):
         outs.append((out.copy(), resid.cpu().numpy()))
     for o, r in outs[1:]:
         assert np.array_equal(o, outs[0][0]) and np.array_equal(r, outs[0][1])
+
+
+# --------------------------------------------------------------------------------------------------
+# K3: CSR SpMV variants (CSR-bulk ring fed by cp.async.bulk, CSR-stream, row per sub-warp)
+# --------------------------------------------------------------------------------------------------
+def _ragged_csr(nrows, seed, heavy_block=False, empty_rows=True):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(0 if empty_rows else 1, 8, size=nrows)
+    if heavy_block and nrows > 600:
+        cnt[256:512] = 23          # one 256-row block holds far more entries than one ring slot (several chunks)
+        cnt[520:900:3] = 0
+    rowptr = np.zeros(nrows + 1, dtype=np.int64)
+    np.cumsum(cnt, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    col = rng.integers(0, nrows, size=nnz).astype(np.int32)
+    val = rng.uniform(-1, 1, size=nnz)
+    return sp.csr_matrix((val, col, rowptr.astype(np.int32)), shape=(nrows, nrows))
+
+
+@pytest.mark.parametrize("nrows,seed,heavy", [(1, 0, False), (37, 1, False), (255, 2, False), (256, 3, False),
+                                               (257, 4, False), (1000, 5, True), (4099, 6, True), (65536, 7, False),
+                                               (300001, 8, True)])
+def test_csr_spmv_variants_ragged(ab, nrows, seed, heavy):
+    import torch
+    S = _ragged_csr(nrows, seed, heavy)
+    if S.nnz == 0:
+        S = _ragged_csr(nrows, seed, heavy, empty_rows=False)
+    # scipy's canonical form would merge duplicates; keep the raw arrays
+    rowptr = torch.from_numpy(S.indptr.astype(np.int32)).cuda()
+    col = torch.from_numpy(S.indices.astype(np.int32)).cuda()
+    val = torch.from_numpy(S.data.copy()).cuda()
+    x = torch.from_numpy(np.random.default_rng(seed + 100).uniform(-1, 1, nrows)).cuda()
+    # row sums in entry order, as the reference's av would form them
+    ref = np.zeros(nrows)
+    xs = x.cpu().numpy()
+    prod = S.data * xs[S.indices]
+    for r in range(min(nrows, 5000)):
+        acc = 0.0
+        for p in range(S.indptr[r], S.indptr[r + 1]):
+            acc += prod[p]
+        ref[r] = acc
+    L = ab.lib()
+    out = {}
+    try:
+        for variant in (0, 1, 2):
+            L.ab200_set_spmv_variant(variant)
+            y = torch.full((nrows,), float("nan"), dtype=torch.float64, device="cuda")
+            assert L.ab200_csr_spmv_f64(nrows, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(),
+                                        y.data_ptr()) == 0
+            torch.cuda.synchronize()
+            out[variant] = y.cpu().numpy()
+    finally:
+        L.ab200_set_spmv_variant(0)
+    m = min(nrows, 5000)
+    assert np.array_equal(out[0][:m], ref[:m])          # bulk: in-order row sums, bit for bit
+    assert np.array_equal(out[0], out[1])               # bulk == stream everywhere
+    full = S @ xs
+    assert np.allclose(out[2], full, rtol=1e-13, atol=1e-14)
+    assert np.allclose(out[0], full, rtol=1e-13, atol=1e-14)
+
+
+def test_csr_spmv_bulk_unaligned_arrays_fall_back(ab):
+    """cp.async.bulk needs 16-byte aligned sources: arrays that are not must still give the same product."""
+    import torch
+    S = _ragged_csr(3000, 11)
+    n = 3000
+    colbuf = torch.zeros(S.nnz + 1, dtype=torch.int32, device="cuda")
+    colbuf[1:] = torch.from_numpy(S.indices.astype(np.int32)).cuda()
+    col = colbuf[1:]                                     # 4-byte aligned only
+    rowptr = torch.from_numpy(S.indptr.astype(np.int32)).cuda()
+    val = torch.from_numpy(S.data.copy()).cuda()
+    x = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, n)).cuda()
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert col.data_ptr() % 16 != 0
+    assert ab.lib().ab200_csr_spmv_f64(n, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(),
+                                       y.data_ptr()) == 0
+    assert np.allclose(y.cpu().numpy(), S @ x.cpu().numpy(), rtol=1e-13, atol=1e-14)
+
+
+def test_csr_spmv_f32_bulk(ab):
+    import torch
+    S = _ragged_csr(70001, 12, heavy_block=True).astype(np.float32)
+    n = S.shape[0]
+    rowptr = torch.from_numpy(S.indptr.astype(np.int32)).cuda()
+    col = torch.from_numpy(S.indices.astype(np.int32)).cuda()
+    val = torch.from_numpy(S.data.copy()).cuda()
+    x = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)).cuda()
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    assert ab.lib().ab200_csr_spmv_f32(n, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(),
+                                       y.data_ptr()) == 0
+    assert np.allclose(y.cpu().numpy(), S @ x.cpu().numpy(), rtol=2e-5, atol=2e-6)

@@ -260,3 +260,66 @@ def test_oracle_shift_invert_and_generalized():
     r = Oracle().solve(op2, n, 4, 10, "LM", tol=0.0, mxiter=300, mode=2, bmat="G", bop=lambda x: M @ x)
     assert r.info == 0 and r.ierr == 0
     assert np.abs(np.sort(r.d) - gev[-4:]).max() < 1e-8
+
+
+# ----------------------------------------------------------------------------------------------------
+# Independent cross-check: SciPy >= 1.15 ships its own C translation of ARPACK-NG's [ds]saupd/[ds]naupd
+# (scipy/sparse/linalg/_eigen/arpack/_arpacklib) -- a second, unrelated restatement of the same Fortran.
+# With the same start vector both must take the same path: restart count, OP*x count, nconv, eigenvalues.
+# ----------------------------------------------------------------------------------------------------
+def _scipy_arpack(sym, A, n, nev, ncv, which, r0, tol, tp="d", maxiter=3000):
+    import importlib
+    mod = importlib.import_module("scipy.sparse.linalg._eigen.arpack.arpack")
+    if not hasattr(mod, "_arpacklib"):
+        pytest.skip("this SciPy does not ship the C translation of ARPACK")
+    cls = mod._SymmetricArpackParams if sym else mod._UnsymmetricArpackParams
+    P = cls(n, nev, tp, lambda x: A @ x, ncv=ncv, v0=r0.astype(np.float64 if tp == "d" else np.float32).copy(),
+            maxiter=maxiter, which=which, tol=tol)
+    nopx = 0
+    while not P.converged:
+        P.iterate()
+        nopx += P.arpack_dict["ido"] in (1, 5)
+    vals = P.extract(False)
+    return dict(nconv=int(P.arpack_dict["nconv"]), restarts=int(P.arpack_dict["iter"]), nopx=int(nopx),
+                vals=np.asarray(vals))
+
+
+@pytest.mark.parametrize("which", ["LA", "SA", "LM", "SM", "BE"])
+def test_oracle_follows_scipy_arpack_translation_sym(which):
+    from problems import laplace2d
+    A = laplace2d(17, 13)
+    n = A.shape[0]
+    r0 = np.random.default_rng(7).uniform(-1, 1, n)
+    s = _scipy_arpack(True, A, n, 5, 18, which, r0, 1e-10)
+    b = Oracle().solve(lambda x: A @ x, n, 5, 18, which, tol=1e-10, mxiter=3000, resid=r0)
+    assert (s["nconv"], s["restarts"], s["nopx"]) == (int(b.nconv), int(b.iparam[2]), int(b.iparam[8]))
+    assert np.abs(np.sort(s["vals"]) - np.sort(b.d)).max() < 1e-12 * np.abs(b.d).max()
+
+
+@pytest.mark.parametrize("which", ["LM", "LR", "SR", "SM"])
+def test_oracle_follows_scipy_arpack_translation_nonsym(which):
+    from problems import convdiff2d
+    A = convdiff2d(14, rho=10.0)
+    n = A.shape[0]
+    r0 = np.random.default_rng(7).uniform(-1, 1, n)
+    s = _scipy_arpack(False, A, n, 4, 16, which, r0, 1e-10)
+    b = Oracle().solve(lambda x: A @ x, n, 4, 16, which, sym=False, tol=1e-10, mxiter=3000, resid=r0)
+    assert (s["nconv"], s["restarts"], s["nopx"]) == (int(b.nconv), int(b.iparam[2]), int(b.iparam[8]))
+    ev = np.sort_complex(b.dr[:4] + 1j * b.di[:4])
+    assert np.abs(np.sort_complex(np.asarray(s["vals"], dtype=complex))[:4] - ev).max() < 1e-10 * np.abs(ev).max()
+
+
+def test_oracle_follows_scipy_arpack_translation_larger_and_float():
+    from problems import laplace2d
+    A = laplace2d(60, 45)
+    n = A.shape[0]
+    r0 = np.random.default_rng(21).uniform(-1, 1, n)
+    s = _scipy_arpack(True, A, n, 8, 30, "LA", r0, 1e-12)
+    b = Oracle().solve(lambda x: A @ x, n, 8, 30, "LA", tol=1e-12, mxiter=3000, resid=r0)
+    assert (s["nconv"], s["restarts"], s["nopx"]) == (int(b.nconv), int(b.iparam[2]), int(b.iparam[8]))
+    assert np.abs(np.sort(s["vals"]) - np.sort(b.d)).max() < 1e-12 * np.abs(b.d).max()
+    A32 = A.astype(np.float32)
+    s = _scipy_arpack(True, A32, n, 4, 16, "LA", r0, 1e-4, tp="f")
+    b = Oracle().solve(lambda x: A32 @ x, n, 4, 16, "LA", tol=1e-4, mxiter=3000, resid=r0, dtype=np.float32)
+    assert s["nconv"] == int(b.nconv) == 4
+    assert np.abs(np.sort(s["vals"]) - np.sort(b.d)).max() < 1e-4 * np.abs(b.d).max()
