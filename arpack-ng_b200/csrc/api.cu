@@ -157,6 +157,7 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
     auto it = registered_ops<T>().find(key);
     if (it == registered_ops<T>().end()) return;
     d = it->second;
+    registered_ops<T>().erase(it);  // one-shot: a later solve that reuses this workl address starts unregistered
   }
   if (d.nrows != n) throw CudaError("registered CSR operator has a different row count than the solve");
   CudaVecOps<T>* ops = c->ops.get();
@@ -201,6 +202,9 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
       if (!par && iparam[6] == 1 && bmat[0] == 'I') {
         if (SYM) attach_registered_op<T>(c, c->sym.get(), workl, n);
         else attach_registered_op<T>(c, c->nonsym.get(), workl, n);
+      } else {
+        std::lock_guard<std::mutex> lk(g_mu);
+        registered_ops<T>().erase(workl);  // not applicable to this solve (PARPACK, bmat='G', modes 2-5)
       }
       if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
     } else {

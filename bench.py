@@ -290,6 +290,8 @@ def run_ours(args):
         for _ in range(e2e_steps):
             rr = one_solve(host_buffers=True, resid=r0h)
             nop2 += int(rr.iparam[8])
+            if rr.nsteps != int(rr.iparam[8]):
+                raise SystemExit("bench.py: e2e solve did not hand every OP*x to the caller")
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         per = nop2 // e2e_steps
@@ -361,7 +363,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096)
-    ap.add_argument("--restarts", type=int, default=4)
+    ap.add_argument("--restarts", type=int, default=20,
+                    help="restart budget of one bench step (SURVEY.md 8d: a fixed 20-restart window)")
     ap.add_argument("--workload", default="laplace2d", choices=["laplace2d", "laplace3d"],
                     help="laplace2d = BASELINE config 2 (default, the headline); laplace3d = config 3 (use --nx 512)")
     ap.add_argument("--op-mode", default="rci", choices=["rci", "registered"],

@@ -136,7 +136,9 @@ void ab200_reset_seed(void);
 /* Registered-operator mode (opt-in; strict RCI stays the default): the library applies y = A x (square CSR matrix in
  * HBM, int32 indices) itself for the solve keyed to `workl` (mode 1, bmat 'I'), so one *aupd_c call runs the whole solve
  * -- the loop of EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:787-846 without a host round trip per step.  K1+K2 are folded
- * into the SpMV and alpha = v^T OP v, ||OP v||^2 come out of its epilogue.  nrows = 0 unregisters. */
+ * into the SpMV and alpha = v^T OP v, ||OP v||^2 come out of its epilogue.  The registration is ONE-SHOT: it is consumed
+ * by the next ido = 0 call with this workl (and dropped there if the solve is not mode 1 / bmat 'I' / sequential), so a
+ * later solve that happens to reuse the address runs the plain protocol.  nrows = 0 unregisters. */
 int ab200_register_csr_op_f64(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
                               const double* val);
 int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,

@@ -300,3 +300,21 @@ def test_registered_operator_row_count_mismatch_fails_loudly(ab):
     A = ab.CsrOperator.laplace2d(20, 20)
     with pytest.raises(ab.ArpackB200Error):   # info = -9990 from the C-ABI, surfaced by the binding
         ab.solve(None, A.n - 1, 3, 12, "LA", tol=1e-8, mxiter=10, registered_op=A, eupd=False)
+
+
+def test_registration_is_one_shot(ab):
+    """A registration is consumed by the solve it was made for: the next solve on the same workl address hands every
+    OP*x back to the caller again."""
+    A = ab.CsrOperator.laplace2d(31, 23)
+    r0 = np.random.default_rng(2).uniform(-1, 1, A.n)
+    for _ in range(6):   # numpy reuses the freed workl block: same address, no registration pending
+        a = ab.solve(None, A.n, 3, 12, "LA", tol=1e-8, mxiter=500, resid=r0, registered_op=A)
+        b = ab.solve(A, A.n, 3, 12, "LA", tol=1e-8, mxiter=500, resid=r0)
+        assert a.nsteps == 0 and b.nsteps == int(b.iparam[8]) > 0
+        assert np.abs(a.d - b.d).max() <= RTOL64 * np.abs(b.d).max()
+    # an explicit stale registration on an address a non-applicable solve uses is dropped, not kept
+    L = ab.lib()
+    w = np.zeros(12 * 12 + 8 * 12)
+    assert L.ab200_register_csr_op_f64(w.ctypes.data, A.n, A.nnz, A.rowptr.data_ptr(), A.col.data_ptr(),
+                                       A.val.data_ptr()) == 0
+    assert L.ab200_register_csr_op_f64(w.ctypes.data, 0, 0, None, None, None) == 0
