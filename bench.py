@@ -317,15 +317,20 @@ def run_ours(args):
         total_ms = sum(v["ms"] for v in prof.values())
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
         traffic = None
+        traffic_ref = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(name, {}).get("dram_bytes_per_launch")
+                ent = json.load(open(tp)).get(name, {})
+                traffic = ent.get("dram_bytes_per_launch")
+                # the ncu capture is one launch at a fixed column count j; its algorithmic bytes are recorded with it
+                traffic_ref = {"algorithmic_bytes_at_capture": ent.get("algorithmic_bytes_at_capture"),
+                               "traffic_over_algorithmic": ent.get("traffic_over_algorithmic")}
             except Exception:
                 traffic = None
         step_bytes = sum(v["bytes"] for v in prof.values())
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "launches": top["launches"],
+                "traffic": traffic, "traffic_ref": traffic_ref, "peak_source": peak_src, "launches": top["launches"],
                 "avg_launch_ms": top["ms"] / max(1, top["launches"]), "share_of_kernel_time": top["ms"] / total_ms,
                 "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
                 "all_kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),

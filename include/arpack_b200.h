@@ -194,6 +194,20 @@ int ab200_fill_hash_f64(long long n, long long i0, unsigned long long seed, doub
 int ab200_residuals_f64(int n, const int* rowptr, const int* col, const double* val, int k, const double* z,
                         long long ldz, const double* d_host, double* out_host);
 
+
+/* ---- on-disk formats of the tool layer (host only, no CUDA; EXAMPLES/MATRIX_MARKET/arpackSolver.hpp) ---- */
+/* Coordinate file with the reader semantics of arpackSolver.hpp:361-416: '%' comments and blank lines skipped, header
+ * "n m [nnz]", body "i j value", 1-based when max(i) == n or max(j) == m else 0-based; returned as CSR (malloc'ed,
+ * release with ab200_mm_free) with column-sorted rows and duplicates summed (Eigen setFromTriplets, :417-424).
+ * Returns 0, 1 cannot open, 2 bad header, 3 bad line, 4 index out of range, 5 too large for int32, 6 out of memory. */
+int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
+                      double** val_host);
+void ab200_mm_free(void* p);
+/* the --restart dump of arpackSolver.hpp:664-704: "count" then one value per line; load fails (2) on a count
+ * mismatch and, with allow_zero = 0, replaces |value| < 1e-6 by machine epsilon (resid must not be zero) */
+int ab200_restart_save_f64(const char* path, long long count, const double* values);
+int ab200_restart_load_f64(const char* path, long long count, double* values, int allow_zero);
+
 #ifdef __cplusplus
 }
 #endif
