@@ -266,7 +266,10 @@ class IrlBase {
       if (!ai_fused_op_) {
         const T tiny = tiny_norm();
         if (rnorm_ >= tiny) {
-          ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(ai_j_), slot(ivj()), slot(IPJ), bmat_ == 'I');
+          // mode 1 / bmat 'I': the B*x slot is neither read by this code nor part of the hand-off (ipntr(3) is
+          // documented for the shift-invert modes only), so the third store of K2 is skipped
+          ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(ai_j_), slot(ivj()),
+                           (bmat_ == 'I' && mode_ == 1) ? nullptr : slot(IPJ), bmat_ == 'I');
         } else {
           // dlascl fallback of the reference (dsaitr.f:450-453): scale in two safe steps
           const T big = std::ldexp(T(1), sizeof(T) == 8 ? 500 : 60);

@@ -238,6 +238,164 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
 }
 
 // ---------------------------------------------------------------------------------------------
+// UPD / UPD_SPEC, second form: rows belong to lanes.  Warp gw of a group owns rows 16*gw .. 16*gw+15 of the
+// tile; lane l works on row (l & 15) and on the columns of parity (l >> 4).  The row-local product V(i,:)*coef is
+// finished inside the warp with one shuffle, so r(i) is known without a group barrier or a trip through shared
+// memory, and the speculative dots s[c] += V(i,c)*r(i) accumulate in registers (KB = ceil(j/2) per lane), reduced
+// across lanes and warps once per kernel.  Same ring, same producer, same aux layout as k_orth.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool SPEC, int KB>
+__global__ void __launch_bounds__(kThreadsTma, 1)
+k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  if (!SPEC && p.pred_w2 != nullptr) {
+    // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
+    const T wn = sqrt(*p.pred_w2), rn = sqrt(*p.pred_r2);
+    if (rn > T(0.717f) * wn) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.flag_out) *p.flag_out = T(0);
+      return;
+    }
+  }
+  T* tiles = reinterpret_cast<T*>(smem);
+  unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
+  T* wsum = reinterpret_cast<T*>(aux);                   // [NG*NCW warps][MAXB*CB columns]  (== NG*4*R elements)
+  T* cs = wsum + NG * 4 * R;                             // [MAXB*CB] coefficients
+  T* wnrm = cs + MAXB * CB;                              // [NG*NCW] per-warp ||r||^2
+  uint64_t* full = reinterpret_cast<uint64_t*>(wnrm + MAXB * CB + 8);
+  uint64_t* empty = full + MAXST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NCW);
+    }
+    mbar_fence_init();
+  }
+  for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
+  __syncthreads();
+
+  const int64_t ntiles = (p.n + R - 1) / R;
+  const uint32_t stage_elems = p.stage_bytes / sizeof(T);
+  const uint32_t v_bytes = (uint32_t)p.nboxes * p.box_bytes;
+
+  if (warp == NG * NCW) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = v_bytes + (p.x_tma ? (uint32_t)(R * sizeof(T)) : 0u);
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(empty + s, ph ^ 1u);
+        mbar_expect_tx(full + s, tx_bytes);
+        const uint32_t dst = smem_u32(tiles) + (uint32_t)s * p.stage_bytes;
+        for (int b = 0; b < p.nboxes; ++b) load_2d(dst + (uint32_t)b * p.box_bytes, &tmap, (int)(t * R), b * CB, full + s);
+        if (p.x_tma) load_1d(dst + v_bytes, &xmap, (int)(t * R), full + s);
+        if (++s == p.nstages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int g = warp / NCW, gw = warp - g * NCW;
+    const int half = lane >> 4, row = gw * 16 + (lane & 15);
+    T acc[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) acc[k] = T(0);
+    T accn = T(0);
+    T xn = T(0);
+    if (!p.x_tma) {
+      const int64_t r = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * R + row;
+      xn = (r < p.n) ? p.x[r] : T(0);
+    }
+    int s = g;
+    uint32_t ph = 0;
+    const int j = p.j;
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x) {
+      const int64_t row0 = t * R;
+      T xv = xn;
+      if (!p.x_tma) {
+        const int64_t r = row0 + (int64_t)NG * gridDim.x * R + row;
+        xn = (r < p.n) ? p.x[r] : T(0);
+      }
+      mbar_wait(full + s, ph);
+      const T* tr = tiles + (size_t)s * stage_elems + row;
+      if (p.x_tma) xv = tr[v_bytes / sizeof(T)];
+      // phase 1: my half of the columns of my row, two chains; the other half comes over one shuffle
+      T a0 = T(0), a1 = T(0);
+      constexpr bool kKeep = SPEC && KB <= 16;  // few enough columns: the row stays in registers for phase 2
+      T keep[kKeep ? KB : 1];
+      if (kKeep) {
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          const int cc = 2 * k + half;
+          const T vv = (cc < j) ? tr[cc * R] : T(0);
+          keep[k] = vv;
+          if (k & 1) a1 += vv * cs[cc];   // cs is zero-padded up to MAXB*CB
+          else a0 += vv * cs[cc];
+        }
+      } else {
+        int c = half;
+#pragma unroll 4
+        for (; c + 2 < j; c += 4) {
+          a0 += tr[c * R] * cs[c];
+          a1 += tr[(c + 2) * R] * cs[c + 2];
+        }
+        if (c < j) a0 += tr[c * R] * cs[c];
+      }
+      T a = a0 + a1;
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      const T rv = xv - a;
+      if (half == 0) {
+        const int64_t r = row0 + row;
+        if (r < p.n) p.dst[r] = rv;
+        accn += rv * rv;
+      }
+      if (SPEC) {
+        // phase 2: s[c] += V(i,c) * r(i) for my columns (registers, or the tile that is still in shared memory)
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          const int cc = 2 * k + half;
+          if (kKeep) acc[k] += keep[k] * rv;
+          else if (cc < j) acc[k] += tr[cc * R] * rv;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+      s += NG;
+      if (s >= p.nstages) { s -= p.nstages; ph ^= 1u; }
+    }
+    // once per kernel: lanes -> warp (fixed xor tree over the 16 rows), warps -> CTA (fixed order), CTA partial
+    accn = warp_sum(accn);
+    if (lane == 0) wnrm[warp] = accn;
+    if (SPEC) {
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        T v = acc[k];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if ((lane & 15) == 0 && 2 * k + half < MAXB * CB) wsum[warp * (MAXB * CB) + 2 * k + half] = v;
+      }
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(NG * NCW * 32) : "memory");
+    T* mine = p.partial + (size_t)blockIdx.x * p.pcols;
+    if (SPEC && tid < j) {
+      T sum = T(0);
+#pragma unroll
+      for (int w = 0; w < NG * NCW; ++w) sum += wsum[w * (MAXB * CB) + tid];
+      mine[tid] = sum;
+    }
+    if (tid == NG * NCW * 32 - 1 && p.out != nullptr) {
+      T sum = T(0);
+#pragma unroll
+      for (int w = 0; w < NG * NCW; ++w) sum += wnrm[w];
+      mine[SPEC ? j : 0] = sum;
+    }
+  }
+  if (p.out == nullptr) return;
+  if (!SPEC && blockIdx.x == 0 && tid == 0 && p.flag_out) *p.flag_out = T(1);
+  finish_grid_reduce(p.partial, p.pcols, SPEC ? p.j + 1 : 1, p.out, p.ticket);
+}
+
+// ---------------------------------------------------------------------------------------------
 // VQ: out(:,0:kout) = V(:,0:kin) * Q.  Each consumer group owns a 128-row tile; a warp computes a
 // register block of (32*RPL rows) x (4 columns): RPL V values per lane and four Q entries (broadcast
 // from shared memory) feed 4*RPL FP64 FMAs per k, which keeps the shared-memory traffic below the HBM
@@ -446,6 +604,51 @@ bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, Orth
   return true;
 }
 
+template <typename T, bool SPEC, int KB>
+bool launch_upd_kb(cudaStream_t stream, int grid, size_t smem, const CUtensorMap& map, const CUtensorMap& xmap,
+                   const OrthParams<T>& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_upd<T, SPEC, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kTileBudget + aux_bytes<T>())) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  k_upd<T, SPEC, KB><<<grid, kThreadsTma, smem, stream>>>(map, xmap, p);
+  return true;
+}
+
+// UPD / UPD_SPEC through k_upd (rows per lane); AB200_UPD=old keeps the k_orth form for A/B measurements
+template <typename T, bool SPEC>
+bool launch_upd(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, OrthParams<T>& p, const char* name,
+                double bytes) {
+  static const bool old_form = getenv("AB200_UPD") && std::strcmp(getenv("AB200_UPD"), "old") == 0;
+  if (old_form) return launch_orth<T, SPEC ? UPD_SPEC : UPD>(stream, num_sms, v, ldv, p, name, bytes);
+  CUtensorMap map, xmap;
+  if (!get_tensor_map(&map, v, (int)sizeof(T), p.n, ldv, p.j, R, CB)) return false;
+  if (p.x_tma) {
+    if (!get_tensor_map(&xmap, p.x, (int)sizeof(T), p.n, 0, 0, R, 0)) return false;
+  } else {
+    xmap = map;
+  }
+  const size_t smem = (size_t)p.nstages * p.stage_bytes + aux_bytes<T>();
+  const int64_t ntiles = (p.n + R - 1) / R;
+  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  ProfScope ps(stream, name, bytes);
+  bool ok;
+  if (!SPEC) ok = launch_upd_kb<T, false, 1>(stream, grid, smem, map, xmap, p);
+  else if (p.j <= 16) ok = launch_upd_kb<T, true, 8>(stream, grid, smem, map, xmap, p);
+  else if (p.j <= 32) ok = launch_upd_kb<T, true, 16>(stream, grid, smem, map, xmap, p);
+  else ok = launch_upd_kb<T, true, 32>(stream, grid, smem, map, xmap, p);
+  if (!ok) return false;
+  launch_stats().kernels++;
+  launch_stats().fast_path++;
+  AB200_CUDA_CHECK(cudaGetLastError());
+  return true;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -498,7 +701,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
     p.x = w; p.dst = resid; p.coef = mbA; p.partial = partial_; p.out = mbB; p.ticket = ticket_;
-    if (!launch_orth<T, UPD_SPEC>(stream_, num_sms_, v, ldv, p, "update_spec_tma", (double)sizeof(T) * n * (j + 2.0)))
+    if (!launch_upd<T, true>(stream_, num_sms_, v, ldv, p, "update_spec_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("update_spec_tma launch failed after dots_tma succeeded");
   }
   allreduce_sum(mbB, (size_t)j + 1);
@@ -510,7 +713,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     p.pcols = 1;
     p.x = resid; p.dst = resid; p.coef = mbB; p.partial = partial_; p.out = mbC; p.ticket = ticket_;
     p.pred_w2 = mbA + j; p.pred_r2 = mbB + j; p.flag_out = mbC + 1;
-    if (!launch_orth<T, UPD>(stream_, num_sms_, v, ldv, p, "reorth_tma", (double)sizeof(T) * n * (j + 2.0)))
+    if (!launch_upd<T, false>(stream_, num_sms_, v, ldv, p, "reorth_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("reorth_tma launch failed after dots_tma succeeded");
   }
   allreduce_sum(mbC, 1);
