@@ -294,19 +294,42 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             raise ArpackB200Error("register_csr_op failed")
         if op is None:
             op = registered_op
-    aupd = dsaupd_c if sym else dnaupd_c
+    # the argument list is the same on every re-entry (the reference's loop passes the same variables each time,
+    # dssimp.f:302-311): marshal it once so that the per-step host cost is one foreign call
+    p_, rt = _prec_of(workl)
+    f_aupd = getattr(L, f"{'p' if comm is not None else ''}{p_}{'saupd' if sym else 'naupd'}_c")
+    cargs = [ido.ctypes.data_as(c_int_p), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(res), ncv, _addr(v),
+             ldv, iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl),
+             int(workl.size), info.ctypes.data_as(c_int_p)]
+    if comm is not None:
+        cargs = [comm] + cargs
+    cargs = tuple(cargs)
+    # operators that accept raw addresses (CsrOperator on device arrays) skip the per-step tensor views
+    fast = getattr(op, "apply_ptr", None) if (not host_buffers and not (mode >= 3 and bmat == "G")) else None
+    if fast is not None and comm is not None:
+        fast = op.apply_halo_ptr if hasattr(op, "halo_lo") else None
+    wbase, isz = _addr(workd), np_dt.itemsize
     nsteps = 0
     while True:
-        aupd(ido, bmat, n, which, nev, tol, res, ncv, v, ldv, iparam, ipntr, workd, workl, info, comm=comm)
-        if ido[0] in (-1, 1):
-            x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
-            y = workd[ipntr[1] - 1: ipntr[1] - 1 + n]
-            if mode >= 3 and bmat == "G" and ido[0] == 1:
-                op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], y, True)
+        f_aupd(*cargs)
+        if info[0] == INFO_DEVICE_ERROR:
+            raise ArpackB200Error("aupd_c: CUDA device error (see stderr); there is no CPU fallback")
+        i = ido[0]
+        if i == 1 or i == -1:
+            if fast is not None:
+                if comm is not None:
+                    fast(comm, wbase + (int(ipntr[0]) - 1) * isz, wbase + (int(ipntr[1]) - 1) * isz)
+                else:
+                    fast(wbase + (int(ipntr[0]) - 1) * isz, wbase + (int(ipntr[1]) - 1) * isz)
             else:
-                op(x, y)
+                x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
+                y = workd[ipntr[1] - 1: ipntr[1] - 1 + n]
+                if mode >= 3 and bmat == "G" and i == 1:
+                    op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], y, True)
+                else:
+                    op(x, y)
             nsteps += 1
-        elif ido[0] == 2:
+        elif i == 2:
             bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n], workd[ipntr[1] - 1: ipntr[1] - 1 + n])
         else:
             break
@@ -342,6 +365,8 @@ class CsrOperator:
         self.n, self.rowptr, self.col, self.val = n, rowptr, col, val
         self.ncols = ncols or n
         self.nnz = int(val.numel())
+        self._spmv_fn = None
+        self._spmv_args = None
 
     @staticmethod
     def laplace2d(nx, ny=None, scale=1.0, device="cuda"):
@@ -408,6 +433,8 @@ class CsrOperator:
 
     def __call__(self, x, y, *_):
         """y = A x; x, y device tensors (views of workd) or host numpy arrays (host-buffer RCI loop)."""
+        if getattr(self, "halo_lo", 0) + getattr(self, "halo_hi", 0) > 0:
+            raise ArpackB200Error("row-partitioned operator: use apply_halo(comm, x, y)")
         L = lib()
         if isinstance(x, np.ndarray):
             rc = L.ab200_csr_spmv_hostvec_f64(self.n, self.ncols, self.rowptr.data_ptr(), self.col.data_ptr(),
@@ -419,6 +446,23 @@ class CsrOperator:
                    y.data_ptr())
         if rc != 0:
             raise ArpackB200Error(f"csr_spmv failed ({rc})")
+
+    def apply_ptr(self, xptr, yptr):
+        """y = A x on raw device addresses (the lean RCI loop of solve())."""
+        f = self._spmv_fn
+        if f is None:
+            import torch
+            L = lib()
+            f = self._spmv_fn = L.ab200_csr_spmv_f64 if self.val.dtype == torch.float64 else L.ab200_csr_spmv_f32
+            self._spmv_args = (self.n, self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr())
+        if f(*self._spmv_args, xptr, yptr) != 0:
+            raise ArpackB200Error("csr_spmv failed")
+
+    def apply_halo_ptr(self, comm, xptr, yptr):
+        if lib().ab200_csr_spmv_halo_f64(comm, self.n, self.halo_lo, self.halo_hi, self.rowptr.data_ptr(),
+                                        self.col.data_ptr(), self.val.data_ptr(), xptr, yptr,
+                                        self.halo.data_ptr()) != 0:
+            raise ArpackB200Error("csr_spmv_halo failed")
 
     def apply_halo(self, comm, x, y):
         rc = lib().ab200_csr_spmv_halo_f64(comm, self.n, self.halo_lo, self.halo_hi, self.rowptr.data_ptr(),

@@ -200,11 +200,7 @@ def run_ours(args):
     else:
         A = ab.CsrOperator.laplace3d(nx, 1, nx, z0=y0, nzloc=nyloc, diag=4.0)
         r0 = ab.hashed_start_vector(A.n, i0=y0 * nx)
-    if world == 1:
-        op = A
-    else:
-        def op(x, y, *_):
-            A.apply_halo(comm, x, y)
+    op = A  # world > 1: solve() applies it with the halo exchange (CsrOperator.apply_halo_ptr) on the library's comm
     n = A.n
     restarts = args.restarts
 
