@@ -67,6 +67,7 @@ class IrlBase {
   const Counters& counters() const { return cnt; }
   // largest relative disagreement between the SpMV-epilogue dots and the CGS sweep (registered-operator mode)
   T fused_dot_maxdiff = 0;
+  long long speculative_hits() const { return cnt_spec_hits_; }  // steps whose K1+K2 ran ahead of the host fetch
   void set_registered_op(std::function<void(const T*, T*)> op,
                          std::function<bool(T, const T*, T*, T*, T*)> fused) {
     op_ = std::move(op);
@@ -116,6 +117,10 @@ class IrlBase {
   std::function<void(const T* x, T* y)> op_;
   std::function<bool(T inv, const T* resid, T* vj, T* y, T* mb_dots)> fused_op_;
   bool ai_fused_op_ = false;
+  bool ai_spec_hit_ = false;
+  bool spec_issued_ = false;   // a speculative K1+K2 for the next step is in the stream
+  T spec_rnorm_ = 0;           // the norm it scaled with
+  long long cnt_spec_hits_ = 0;
 
   T* vcol(int j1) { return v_ + (int64_t)(j1 - 1) * ldv_; }  // 1-based column
   T* slot(int off1) { return workd_ + (off1 - 1); }           // 1-based workd offset
@@ -238,6 +243,7 @@ class IrlBase {
   bool extend() {
     CO_BEGIN(ai_pc_)
     ai_info_ = 0;
+    spec_issued_ = false;
     for (ai_j_ = ai_k_ + 1; ai_j_ <= ai_k_ + ai_np_; ++ai_j_) {
       ai_beta_ = rnorm_;
       ai_rstart_ = false;
@@ -259,11 +265,18 @@ class IrlBase {
       }
       // v_j = r/||r||, p_j = B r/||r||, x = v_j   (dsaitr.f:438-468)
       ai_fused_op_ = false;
+      // K1+K2 of this step may already have been issued speculatively behind the previous step's kernels (see below):
+      // valid when the host arrived at exactly the norm the device used and took no restart / rescaling path
+      ai_spec_hit_ = spec_issued_ && !ai_rstart_ && rnorm_ == spec_rnorm_ && rnorm_ >= tiny_norm();
+      spec_issued_ = false;
+      if (ai_spec_hit_) {
+        cnt_spec_hits_++;
+      } else
       if (fused_op_ && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm()) {
         // registered operator: K1+K2+K3 in one kernel (v_j written on the way, x never materialised)
         ai_fused_op_ = fused_op_(T(1) / rnorm_, resid_, vcol(ai_j_), slot(irj()), mbC() + 2);
       }
-      if (!ai_fused_op_) {
+      if (!ai_fused_op_ && !ai_spec_hit_) {
         const T tiny = tiny_norm();
         if (rnorm_ >= tiny) {
           // mode 1 / bmat 'I': the B*x slot is neither read by this code nor part of the hand-off (ipntr(3) is
@@ -292,7 +305,17 @@ class IrlBase {
       if (bmat_ == 'I' && mode_ != 2) {
         // ---- fused path: CGS + speculative DGKS, one host round trip (K4..K10) ----
         ops_->orth_step(n_, ai_j_, v_, ldv_, slot(irj()), resid_, mbA(), mbB(), mbC());
-        ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
+        if (ai_j_ < ai_k_ + ai_np_ && !fused_op_) {
+          // not the last step of the sweep: issue the next step's v_{j+1} = r/||r|| now, with the norm taken from
+          // the device mailbox, so that the device is busy while the host reads the mailbox and decides
+          ops_->mark_fetch_point();
+          spec_issued_ = ops_->start_step_speculative(n_, ai_j_, mbB(), mbC(), tiny_norm(), resid_, vcol(ai_j_ + 1),
+                                                      slot(ivj()), (bmat_ == 'I' && mode_ == 1) ? nullptr : slot(IPJ));
+          ops_->fetch_marked(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
+          if (spec_issued_) spec_rnorm_ = std::sqrt((hC()[1] != T(0)) ? hC()[0] : hB()[ai_j_]);
+        } else {
+          ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
+        }
         if (ai_fused_op_) {
           // alpha = v_j^T OP v_j and ||OP v_j||^2 from the SpMV epilogue must agree with the CGS sweep
           const T da = std::fabs(hC()[2] - hA()[ai_j_ - 1]), dw = std::fabs(hC()[3] - hA()[ai_j_]);

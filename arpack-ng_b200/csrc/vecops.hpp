@@ -59,6 +59,18 @@ struct VecOps {
   // (for bmat='I' pass bx_from_resid=true to write bx = resid*inv instead of scaling in place)
   virtual void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx,
                           bool bx_from_resid) = 0;
+  // Speculative K1+K2 of the NEXT step, enqueued before the host has read the mailbox of the orth_step just issued:
+  // the scale is formed on the device, inv = 1/sqrt(mbC[1] != 0 ? mbC[0] : mbB[j]) -- the value the host will derive
+  // in the common path -- and nothing is written when that norm is below `tiny`.  Lets the device work through the
+  // host round trip of fetch_marked().  Returns false when the backend does not support it.
+  virtual bool start_step_speculative(int64_t /*n*/, int /*j*/, const T* /*mbB*/, const T* /*mbC*/, T /*tiny*/,
+                                      const T* /*resid*/, T* /*vj*/, T* /*out_x*/, T* /*bx*/) {
+    return false;
+  }
+  // mark_fetch_point(): remember the current end of the stream; fetch_marked(): like fetch(), but waits only for
+  // the work enqueued before the mark (so kernels issued after it keep running during the copy)
+  virtual void mark_fetch_point() {}
+  virtual void fetch_marked(T* host_dst, const T* mb, size_t count) { fetch(host_dst, mb, count); }
   // rank-1 purification Z(:,0:k) += resid * w^T  (dseupd.f:857); w is a host vector
   virtual void ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) = 0;
 

@@ -8,6 +8,7 @@
 // Reference call sites replaced: K1/K2 start_step, K5/K6 dots, K7/K8 update,
 // K9/K10 conditional re-orthogonalisation, K12-K16 vq, K17 larnv, K21 ger.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "vecops_cuda.cuh"
@@ -297,6 +298,23 @@ __global__ void k_start_step(int64_t n, T inv, const T* __restrict__ resid, T* _
   }
 }
 
+// speculative K1+K2: the scale comes from the mailbox of the orthogonalisation that precedes it on the stream
+template <typename T>
+__global__ void k_start_step_spec(int64_t n, const T* __restrict__ nrm2_plain, const T* __restrict__ nrm2_reorth,
+                                  const T* __restrict__ flag, T tiny, const T* __restrict__ resid, T* __restrict__ vj,
+                                  T* __restrict__ outx, T* bx) {
+  const T val = (*flag != T(0)) ? *nrm2_reorth : *nrm2_plain;
+  const T rn = sqrt(val);
+  if (!(rn >= tiny) || !(rn > T(0))) return;  // the host takes the restart / rescaling path and redoes this step
+  const T inv = T(1) / rn;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const T t = resid[r] * inv;
+    vj[r] = t;
+    outx[r] = t;
+    if (bx != nullptr) bx[r] = t;
+  }
+}
+
 // K21: Z(:,0:k) += resid * w^T
 template <typename T>
 __global__ void k_ger(int64_t n, int k, const T* __restrict__ resid, const T* __restrict__ w, T* z, int64_t ldz) {
@@ -451,6 +469,8 @@ CudaVecOps<T>::~CudaVecOps() {
   cudaFree(ticket_);
   cudaFree(qbuf_);
   cudaFreeHost(qpinned_);
+  if (mark_event_) cudaEventDestroy(mark_event_);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
 
 template <typename T>
@@ -647,6 +667,39 @@ void CudaVecOps<T>::start_step(int64_t n, T inv, const T* resid, T* vj, T* outx,
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? (from_resid ? 4.0 : 5.0) : 3.0));
   k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid);
   AB200_LAUNCHED();
+}
+template <typename T>
+bool CudaVecOps<T>::start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj,
+                                           T* outx, T* bx) {
+  static const bool off = getenv("AB200_SPECULATE") && std::strcmp(getenv("AB200_SPECULATE"), "0") == 0;
+  if (off) return false;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
+  ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? 4.0 : 3.0));
+  k_start_step_spec<T><<<grid, 256, 0, stream_>>>(n, mbB + j, mbC, mbC + 1, tiny, resid, vj, outx, bx);
+  AB200_LAUNCHED();
+  return true;
+}
+template <typename T>
+void CudaVecOps<T>::mark_fetch_point() {
+  if (!copy_stream_) {
+    AB200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    AB200_CUDA_CHECK(cudaEventCreateWithFlags(&mark_event_, cudaEventDisableTiming));
+  }
+  AB200_CUDA_CHECK(cudaEventRecord(mark_event_, stream_));
+  marked_ = true;
+}
+template <typename T>
+void CudaVecOps<T>::fetch_marked(T* host_dst, const T* mb, size_t count) {
+  if (!marked_) {
+    fetch(host_dst, mb, count);
+    return;
+  }
+  marked_ = false;
+  const size_t off = (size_t)(mb - mb_dev_);
+  AB200_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, mark_event_, 0));
+  AB200_CUDA_CHECK(cudaMemcpyAsync(mb_pinned_ + off, mb, sizeof(T) * count, cudaMemcpyDeviceToHost, copy_stream_));
+  AB200_CUDA_CHECK(cudaStreamSynchronize(copy_stream_));
+  std::memcpy(host_dst, mb_pinned_ + off, sizeof(T) * count);
 }
 template <typename T>
 void CudaVecOps<T>::ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) {

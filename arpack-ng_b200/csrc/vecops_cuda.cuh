@@ -106,6 +106,10 @@ class CudaVecOps final : public VecOps<T> {
   void dot(int64_t n, const T* x, const T* y, T* mb_out) override;
   void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
   void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx, bool bx_from_resid) override;
+  bool start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj, T* out_x,
+                              T* bx) override;
+  void mark_fetch_point() override;
+  void fetch_marked(T* host_dst, const T* mb, size_t count) override;
   void ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) override;
 
   void dots(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out) override;
@@ -139,6 +143,10 @@ class CudaVecOps final : public VecOps<T> {
   T* mb_dev_ = nullptr;
   size_t mb_count_ = 0;
   T* mb_pinned_ = nullptr;
+  // side stream + event for fetch_marked(): the mailbox copy overlaps kernels enqueued after the mark
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t mark_event_ = nullptr;
+  bool marked_ = false;
   // two-stage reduction scratch: partial_[grid][pcols_] and a ticket counter
   T* partial_ = nullptr;
   size_t partial_count_ = 0;

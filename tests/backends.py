@@ -228,6 +228,8 @@ def hostdouble_lib():
         L.hd_set_registered_op.argtypes = [C.c_void_p, C.c_int, OP_FN, C.c_int, C.c_int]
         L.hd_fused_dot_maxdiff.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hd_fused_dot_maxdiff.restype = C.c_double
+        L.hd_speculative_hits.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hd_speculative_hits.restype = C.c_longlong
         for p, rp, rt in (("d", c_dbl_p, C.c_double), ("s", c_flt_p, C.c_float)):
             for fam in ("s", "n"):
                 f = getattr(L, f"hd_{p}{fam}aupd")
@@ -285,6 +287,10 @@ class HostDouble(Oracle):
             y[:] = op(x.copy())
         self._opcb = OP_FN(cb) if op is not None else C.cast(None, OP_FN)
         self.L.hd_set_registered_op(self._procs[isd], int(isd), self._opcb, n, int(fused))
+
+    def speculative_hits(self, sym=True, dtype=np.float64):
+        isd = np.dtype(dtype) == np.float64
+        return int(self.L.hd_speculative_hits(self._procs[isd], int(isd), int(sym)))
 
     def fused_dot_maxdiff(self, sym=True, dtype=np.float64):
         isd = np.dtype(dtype) == np.float64

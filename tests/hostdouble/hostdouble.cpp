@@ -90,6 +90,22 @@ struct HostVecOps final : VecOps<T> {
       if (bx) bx[i] = from_resid ? t : bx[i] * inv;
     }
   }
+  unsigned long long spec_calls = 0;
+  bool start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj, T* outx,
+                              T* bx) override {
+    ++spec_calls;
+    const T val = (mbC[1] != T(0)) ? mbC[0] : mbB[j];
+    const T rn = std::sqrt(val);
+    if (!(rn >= tiny) || !(rn > T(0))) return true;
+    const T inv = T(1) / rn;
+    for (int64_t i = 0; i < n; ++i) {
+      const T t = resid[i] * inv;
+      vj[i] = t;
+      outx[i] = t;
+      if (bx) bx[i] = t;
+    }
+    return true;
+  }
   void ger(int64_t n, int k, const T* resid, const T* w, T* z, int64_t ldz) override {
     for (int c = 0; c < k; ++c)
       for (int64_t i = 0; i < n; ++i) z[i + c * ldz] += resid[i] * w[c];
@@ -232,6 +248,11 @@ double hd_fused_dot_maxdiff(void* p, int is_double, int fam_sym) {
   if (is_double) { auto* q = (Proc<double>*)p; return fam_sym ? q->sym->fused_dot_maxdiff : q->nonsym->fused_dot_maxdiff; }
   auto* q = (Proc<float>*)p;
   return fam_sym ? q->sym->fused_dot_maxdiff : q->nonsym->fused_dot_maxdiff;
+}
+long long hd_speculative_hits(void* p, int is_double, int fam_sym) {
+  if (is_double) { auto* q = (Proc<double>*)p; return fam_sym ? q->sym->speculative_hits() : q->nonsym->speculative_hits(); }
+  auto* q = (Proc<float>*)p;
+  return fam_sym ? q->sym->speculative_hits() : q->nonsym->speculative_hits();
 }
 void hd_stats(void* p, int is_double, int fam_sym, int* out5) {
   const Counters* c = nullptr;

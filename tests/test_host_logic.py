@@ -350,3 +350,25 @@ def test_registered_operator_is_ignored_outside_mode1():
     r = hd.solve(lambda x: lu.solve(x), n, 4, 12, "LM", tol=1e-10, mxiter=300, mode=3, sigma=0.0, resid=start(n))
     assert r.info == 0 and r.nsteps > 0
     assert np.allclose(np.sort(r.d), np.sort(np.linalg.eigvalsh(A.toarray()))[:4], rtol=1e-9)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_speculative_start_of_step_hits_and_changes_nothing(sym):
+    """K1+K2 of step j+1 are issued before the host has read step j's mailbox (IrlBase::extend); the scale is taken
+    from the mailbox.  Every step but the first of each sweep must be served that way, with results identical to the
+    oracle's (counts) -- the speculation is invisible."""
+    if sym:
+        A, nev, ncv, which = laplace2d(19, 16), 4, 16, "LA"
+    else:
+        A, nev, ncv, which = convdiff2d(15, rho=10.0), 4, 16, "LM"
+    n = A.shape[0]
+    r0 = start(n, 5)
+    hd = HostDouble()
+    a = hd.solve(lambda x: A @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
+    b = Oracle().solve(lambda x: A @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
+    assert a.info == b.info == 0 and counts(a) == counts(b)
+    hits = hd.speculative_hits(sym)
+    nopx, sweeps = int(a.iparam[8]), int(a.iparam[2]) + 1
+    # every step except the first of a sweep (and the start-vector product) can be speculated
+    assert nopx - 2 * sweeps - 2 <= hits <= nopx
+    assert hits > nopx // 2
