@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* 
 // stream it from global memory chunk by chunk (the CSR-stream scheme) with the slot's val array as scratch.
 template <typename T, int ROWS, int CAP>
 struct SpmvBulkStage {
-  T val[CAP + 4];
-  int col[CAP + 4];
+  T val[CAP];
+  int col[CAP];
   int rp[ROWS + 4];
 };
 
@@ -173,15 +173,15 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, u
                : "memory");
 }
 
-template <typename T, int ROWS, int CAP, int NST, bool FUSED>
+template <typename T, int ROWS, int EPT, int NST, bool FUSED>
 __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const int* __restrict__ rowptr,
                                                              const int* __restrict__ col, const T* __restrict__ val,
                                                              const T* __restrict__ x, T* __restrict__ y, int nloc,
                                                              const T* __restrict__ xh, T xs, T* __restrict__ vj_out,
                                                              T* __restrict__ partial, T* __restrict__ dots_out,
                                                              unsigned int* ticket) {
+  constexpr int CAP = ROWS * EPT;  // entries per ring slot, alignment pad included
   using Stage = SpmvBulkStage<T, ROWS, CAP>;
-  constexpr int EPT = CAP / ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * NST);
@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
     // ---------------- consumers: thread t owns row r0 + t ----------------
     // registers of one block: its entries' columns, values and gathered x, and the owner row's bounds
     struct Item {
-      int cc[EPT];
-      T vv[EPT], xx[EPT];
+      T xx[EPT];
       int rs, re, sidx, p1;
       T xrow;
       bool direct;
@@ -276,17 +275,19 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
       if (it.direct) return;
       int clen = ((it.p1 + 3) & ~3);
       clen = (clen > nnz4 ? nnz4 : clen) - it.sidx;
+      // columns of my entries (the <= 3 tail entries of the matrix were not staged: fetch them into the slot),
+      // then all of my x gathers at once; the values stay in the slot until the products are formed
+      int cc[EPT];
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = tid + k * ROWS;
-        it.cc[k] = 0;
-        it.vv[k] = T(0);
-        if (i < clen) { it.cc[k] = st->col[i]; it.vv[k] = st->val[i]; }
-        else if (i < len) { it.cc[k] = __ldg(col + it.sidx + i); it.vv[k] = __ldg(val + it.sidx + i); }
+        cc[k] = 0;
+        if (i < clen) cc[k] = st->col[i];
+        else if (i < len) { cc[k] = __ldg(col + it.sidx + i); st->val[i] = __ldg(val + it.sidx + i); }
       }
 #pragma unroll
       for (int k = 0; k < EPT; ++k)
-        it.xx[k] = (xh != nullptr && it.cc[k] >= nloc) ? xh[it.cc[k] - nloc] : x[it.cc[k]];
+        it.xx[k] = (xh != nullptr && cc[k] >= nloc) ? xh[cc[k] - nloc] : x[cc[k]];
     };
     int stage = 0;
     uint32_t phase = 0;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
           const int i = tid + k * ROWS;
-          if (i < len) st->val[i] = cur.vv[k] * cur.xx[k];
+          if (i < len) st->val[i] = st->val[i] * cur.xx[k];
         }
       } else {
         // oversized block, streamed from global memory in chunks of CAP entries
@@ -368,13 +369,13 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
   tma::finish_grid_reduce(partial, 2, 2, dots_out, ticket);
 }
 
-template <typename T, int ROWS, int CAP, int NST, bool FUSED>
+template <typename T, int ROWS, int EPT, int NST, bool FUSED>
 int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long nnz, const int* rowptr, const int* col,
                          const T* val, const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial,
                          T* dots_out, unsigned int* ticket) {
-  using Stage = SpmvBulkStage<T, ROWS, CAP>;
+  using Stage = SpmvBulkStage<T, ROWS, ROWS * EPT>;
   constexpr size_t smem = sizeof(Stage) * NST + 2 * NST * sizeof(uint64_t);
-  auto kern = k_csr_spmv_bulk<T, ROWS, CAP, NST, FUSED>;
+  auto kern = k_csr_spmv_bulk<T, ROWS, EPT, NST, FUSED>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -406,16 +407,25 @@ int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr
                      const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out,
                      unsigned int* ticket) {
   static const int variant = getenv("AB200_SPMV_BULK") ? atoi(getenv("AB200_SPMV_BULK")) : 0;
-#define AB200_BULK_CFG(ROWS_, NST_, CTAS_)                                                                         \
-  return launch_spmv_bulk_cfg<T, ROWS_, ROWS_ * 7, NST_, FUSED>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, xh, \
-                                                                xs, vj_out, partial, dots_out, ticket)
+#define AB200_BULK_CFG(ROWS_, EPT_, NST_, CTAS_)                                                                    \
+  return launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, xh, xs,  \
+                                                           vj_out, partial, dots_out, ticket)
+  // entries per thread and ring slot: a 256-row block of a matrix with avg entries per row holds ~256*avg (+3 of
+  // alignment pad); 6 covers 5-point stencils, 8 covers 7-point stencils
+  const double avg = (double)nnz / (double)(nrows > 0 ? nrows : 1);
+  if (avg <= 5.9) {
+    switch (variant) {
+      case 1: AB200_BULK_CFG(128, 6, 3, 6);
+      case 2: AB200_BULK_CFG(256, 6, 2, 4);
+      case 3: AB200_BULK_CFG(256, 6, 4, 2);
+      default: AB200_BULK_CFG(256, 6, 3, 3);
+    }
+  }
   switch (variant) {
-    case 1: AB200_BULK_CFG(128, 3, 6);
-    case 2: AB200_BULK_CFG(256, 2, 4);
-    case 3: AB200_BULK_CFG(256, 4, 2);
-    case 4: AB200_BULK_CFG(512, 2, 2);
-    case 5: AB200_BULK_CFG(128, 2, 8);
-    default: AB200_BULK_CFG(256, 3, 3);
+    case 1: AB200_BULK_CFG(128, 8, 3, 4);
+    case 2: AB200_BULK_CFG(256, 8, 2, 3);
+    case 3: AB200_BULK_CFG(256, 8, 3, 2);
+    default: AB200_BULK_CFG(256, 8, 2, 4);  // measured best on the 7-point Laplacian (5.4 TB/s alone)
   }
 #undef AB200_BULK_CFG
 }
@@ -458,7 +468,7 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   const long long nnz = nnz_hint > 0 ? nnz_hint : 0;
   ProfScope ps(s, "csr_spmv", (double)nnz * (sizeof(T) + 4.0) + (nrows + 1) * 4.0 + 2.0 * nrows * sizeof(T));
   const bool use_stream = spmv_variant() != 2;
-  if (use_stream && avg <= 8.5 && spmv_bulk_ok(rowptr, col, val, nnz))
+  if (use_stream && avg <= 7.9 && spmv_bulk_ok(rowptr, col, val, nnz))
     return launch_spmv_bulk<T, false>(s, nrows, nnz, rowptr, col, val, x, y, nloc, xh, T(1), nullptr, nullptr, nullptr,
                                       nullptr);
   if (use_stream && avg <= 8.5)
@@ -648,7 +658,7 @@ int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* 
                        unsigned int* ticket) {
   if (op.nrows <= 0) return 0;
   const double avg = op.nnz > 0 ? (double)op.nnz / op.nrows : 8.0;
-  if (avg > 8.5) return 1;  // caller falls back to start_step + plain SpMV
+  if (avg > 7.9) return 1;  // caller falls back to start_step + plain SpMV
   cudaStream_t s = cur_stream();
   ProfScope ps(s, "csr_spmv_fused",
                (double)op.nnz * (sizeof(T) + 4.0) + (op.nrows + 1) * 4.0 + 3.0 * op.nrows * sizeof(T));
