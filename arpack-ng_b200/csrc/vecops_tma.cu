@@ -625,7 +625,9 @@ template <typename T, bool SPEC>
 bool launch_upd(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, OrthParams<T>& p, const char* name,
                 double bytes) {
   static const bool old_form = getenv("AB200_UPD") && std::strcmp(getenv("AB200_UPD"), "old") == 0;
-  if (old_form) return launch_orth<T, SPEC ? UPD_SPEC : UPD>(stream, num_sms, v, ldv, p, name, bytes);
+  // beyond 32 columns the row no longer fits in registers between the two phases and the column-per-warp form of
+  // k_orth is the faster one (measured on config 3, ncv = 64: 6.0 vs 5.3 TB/s)
+  if (old_form || (SPEC && p.j > 32)) return launch_orth<T, SPEC ? UPD_SPEC : UPD>(stream, num_sms, v, ldv, p, name, bytes);
   CUtensorMap map, xmap;
   if (!get_tensor_map(&map, v, (int)sizeof(T), p.n, ldv, p.j, R, CB)) return false;
   if (p.x_tma) {
@@ -640,8 +642,7 @@ bool launch_upd(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, OrthP
   bool ok;
   if (!SPEC) ok = launch_upd_kb<T, false, 1>(stream, grid, smem, map, xmap, p);
   else if (p.j <= 16) ok = launch_upd_kb<T, true, 8>(stream, grid, smem, map, xmap, p);
-  else if (p.j <= 32) ok = launch_upd_kb<T, true, 16>(stream, grid, smem, map, xmap, p);
-  else ok = launch_upd_kb<T, true, 32>(stream, grid, smem, map, xmap, p);
+  else ok = launch_upd_kb<T, true, 16>(stream, grid, smem, map, xmap, p);
   if (!ok) return false;
   launch_stats().kernels++;
   launch_stats().fast_path++;
