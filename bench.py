@@ -326,7 +326,9 @@ def run_ours(args):
                 traffic = None
         step_bytes = sum(v["bytes"] for v in prof.values())
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_ref": traffic_ref, "peak_source": peak_src, "launches": top["launches"],
+                "traffic": traffic, "traffic_ref": traffic_ref, "peak_source": peak_src,
+                "peak_note": "the denominator is a measured COPY bandwidth (equal read and write streams); kernels that "
+                             "mostly read (multi-dots, updates of one vector against j columns) can exceed it", "launches": top["launches"],
                 "avg_launch_ms": top["ms"] / max(1, top["launches"]), "share_of_kernel_time": top["ms"] / total_ms,
                 "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
                 "all_kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),

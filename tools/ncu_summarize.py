@@ -53,7 +53,11 @@ def main():
         for r in rows[2:]:
             name = r[ki]
             tag = None
-            if "k_orth" in name:
+            if "k_upd<" in name:
+                tag = "update_spec_tma" if re.search(r"k_upd<[^,]+, (?:\([^)]*\))?(1|true)", name) else "reorth_tma"
+            elif "k_start_step" in name:
+                tag = "start_step"
+            elif "k_orth" in name:
                 m = re.search(r"k_orth<[^,]+, (?:\([^)]*\))?(\d)>", name)
                 tag = {"0": "dots_tma", "1": "reorth_tma", "2": "update_spec_tma"}.get(m.group(1) if m else "", None)
             else:
