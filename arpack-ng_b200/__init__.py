@@ -89,6 +89,7 @@ def lib():
     L.ab200_device_count.restype = C.c_int
     L.ab200_register_csr_op_f64.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
     L.ab200_register_csr_op_f32.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
+    L.ab200_register_csr_halo_op_f64.argtypes = [vp, C.c_int, C.c_int, C.c_longlong, vp, vp, vp, C.c_int, C.c_int, vp]
     L.ab200_fused_dot_maxdiff.argtypes = [vp]
     L.ab200_fused_dot_maxdiff.restype = C.c_double
     L.ab200_kernel_probe_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -288,9 +289,23 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
         # opt-in extension: the library applies the CSR operator itself (one *aupd call per solve)
         if registered_op.val.dtype != t_dt:
             raise ArpackB200Error("registered_op values must have the solve's dtype")
-        reg = L.ab200_register_csr_op_f64 if np_dt == np.float64 else L.ab200_register_csr_op_f32
-        if reg(workl.ctypes.data, registered_op.n, registered_op.nnz, registered_op.rowptr.data_ptr(),
-               registered_op.col.data_ptr(), registered_op.val.data_ptr()) != 0:
+        if comm is not None:
+            # row-partitioned operator: the library also runs the neighbour exchange of the halo planes
+            if np_dt != np.float64:
+                raise ArpackB200Error("halo registration is FP64 only")
+            if not hasattr(registered_op, "halo"):
+                import torch as _t
+                registered_op.halo_lo = registered_op.halo_hi = 0
+                registered_op.halo = _t.zeros(1, dtype=t_dt, device=device)
+            rc = L.ab200_register_csr_halo_op_f64(workl.ctypes.data, comm, registered_op.n, registered_op.nnz,
+                                                  registered_op.rowptr.data_ptr(), registered_op.col.data_ptr(),
+                                                  registered_op.val.data_ptr(), registered_op.halo_lo,
+                                                  registered_op.halo_hi, registered_op.halo.data_ptr())
+        else:
+            reg = L.ab200_register_csr_op_f64 if np_dt == np.float64 else L.ab200_register_csr_op_f32
+            rc = reg(workl.ctypes.data, registered_op.n, registered_op.nnz, registered_op.rowptr.data_ptr(),
+                     registered_op.col.data_ptr(), registered_op.val.data_ptr())
+        if rc != 0:
             raise ArpackB200Error("register_csr_op failed")
         if op is None:
             op = registered_op

@@ -160,6 +160,8 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
     registered_ops<T>().erase(it);  // one-shot: a later solve that reuses this workl address starts unregistered
   }
   if (d.nrows != n) throw CudaError("registered CSR operator has a different row count than the solve");
+  if ((d.comm != 0) != c->par) throw CudaError("registered CSR operator: halo registration needs the p*aupd_c entry "
+                                               "points (and plain registration the sequential ones)");
   CudaVecOps<T>* ops = c->ops.get();
   solver->set_registered_op(
       [d](const T* x, T* y) {
@@ -199,12 +201,12 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
       SeedState* seed = par ? &Globals<T>::seed_par : &Globals<T>::seed;
       if (SYM) c->sym = std::make_unique<IrlSym<T>>(c->ops.get(), par, seed);
       else c->nonsym = std::make_unique<IrlNonsym<T>>(c->ops.get(), par, seed, &Globals<T>::smlnum_first);
-      if (!par && iparam[6] == 1 && bmat[0] == 'I') {
+      if (iparam[6] == 1 && bmat[0] == 'I') {
         if (SYM) attach_registered_op<T>(c, c->sym.get(), workl, n);
         else attach_registered_op<T>(c, c->nonsym.get(), workl, n);
       } else {
         std::lock_guard<std::mutex> lk(g_mu);
-        registered_ops<T>().erase(workl);  // not applicable to this solve (PARPACK, bmat='G', modes 2-5)
+        registered_ops<T>().erase(workl);  // not applicable to this solve (bmat='G', modes 2-5)
       }
       if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
     } else {
@@ -552,6 +554,19 @@ int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const
   CsrOpDesc<float> d;
   d.nrows = nrows; d.nnz = nnz; d.rowptr = rowptr; d.col = col; d.val = val;
   registered_ops<float>()[workl] = d;
+  return 0;
+}
+// The same for a row-partitioned operator under a communicator (pdsaupd_c / pdnaupd_c): nloc local rows, columns >=
+// nloc address halo_buf = [last halo_lo entries of the lower neighbour's x | first halo_hi of the upper one's], which
+// the library fills with an NCCL neighbour exchange before every product (pdsdrv1.f:463-483 inside the library).
+int ab200_register_csr_halo_op_f64(const void* workl, int comm, int nloc, long long nnz, const int* rowptr,
+                                   const int* col, const double* val, int halo_lo, int halo_hi, double* halo_buf) {
+  if (comm_from_handle(comm) == nullptr || nloc <= 0) return -1;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CsrOpDesc<double> d;
+  d.nrows = nloc; d.nnz = nnz; d.rowptr = rowptr; d.col = col; d.val = val;
+  d.comm = comm; d.halo_lo = halo_lo; d.halo_hi = halo_hi; d.halo = halo_buf;
+  registered_ops<double>()[workl] = d;
   return 0;
 }
 // largest relative disagreement between the SpMV-epilogue dots and the CGS sweep in the last registered-op solve

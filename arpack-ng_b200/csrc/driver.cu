@@ -649,8 +649,28 @@ inline int gen_grid(long long n) {
 
 namespace ab200 {
 // C++ entry points used by api.cu for the registered-operator mode (see driver.hpp)
+// halo planes of x for a row-partitioned operator: my first halo_lo entries go down, my last halo_hi go up
+template <typename T>
+int exchange_halo(const CsrOpDesc<T>& op, const T* x) {
+  if (op.comm == 0 || (op.halo_lo == 0 && op.halo_hi == 0)) return 0;
+  try {
+    NcclComm* c = comm_from_handle(op.comm);
+    if (!c) return -1;
+    nccl_halo_exchange(c, x, op.halo, (size_t)op.halo_lo, x + (op.nrows - op.halo_hi), op.halo + op.halo_lo,
+                       (size_t)op.halo_hi, sizeof(T) == 8, cur_stream());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: halo exchange: %s\n", e.what());
+    return -1;
+  }
+  return 0;
+}
+
 template <typename T>
 int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y) {
+  if (op.comm != 0) {
+    if (exchange_halo(op, x) != 0) return -1;
+    return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, op.nrows, op.halo, op.nnz);
+  }
   return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, 0, nullptr, op.nnz);
 }
 template <typename T>
@@ -662,10 +682,19 @@ int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* 
   cudaStream_t s = cur_stream();
   ProfScope ps(s, "csr_spmv_fused",
                (double)op.nnz * (sizeof(T) + 4.0) + (op.nrows + 1) * 4.0 + 3.0 * op.nrows * sizeof(T));
+  // under a communicator the neighbours' planes of the UNSCALED residual are exchanged: the kernel applies 1/||r|| to
+  // the row sums, halo entries included (every rank uses the same global norm); the epilogue dots would be local
+  // partial sums there, so they are not produced
+  const int nloc = op.comm != 0 ? op.nrows : 0;
+  const T* xh = op.comm != 0 ? op.halo : nullptr;
+  if (op.comm != 0) {
+    if (exchange_halo(op, resid) != 0) return -1;
+    dots_out = nullptr;
+  }
   if (spmv_bulk_ok(op.rowptr, op.col, op.val, op.nnz))
-    return launch_spmv_bulk<T, true>(s, op.nrows, op.nnz, op.rowptr, op.col, op.val, resid, y, 0, nullptr, inv, vj,
+    return launch_spmv_bulk<T, true>(s, op.nrows, op.nnz, op.rowptr, op.col, op.val, resid, y, nloc, xh, inv, vj,
                                      partial, dots_out, ticket);
-  return launch_spmv_stream<T, true>(s, op.nrows, op.rowptr, op.col, op.val, resid, y, 0, nullptr, inv, vj, partial,
+  return launch_spmv_stream<T, true>(s, op.nrows, op.rowptr, op.col, op.val, resid, y, nloc, xh, inv, vj, partial,
                                      dots_out, ticket);
 }
 template int csr_op_apply<double>(const CsrOpDesc<double>&, const double*, double*);

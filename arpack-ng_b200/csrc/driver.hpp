@@ -10,6 +10,11 @@ struct CsrOpDesc {
   const int* rowptr = nullptr;
   const int* col = nullptr;
   const T* val = nullptr;
+  // row-partitioned operator under a communicator (PARPACK layout): columns >= nrows address halo[], which holds
+  // the last halo_lo entries of the lower neighbour's x followed by the first halo_hi entries of the upper one's
+  int comm = 0;
+  int halo_lo = 0, halo_hi = 0;
+  T* halo = nullptr;
 };
 
 // y = A x on the library stream

@@ -316,7 +316,7 @@ class IrlBase {
         } else {
           ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
         }
-        if (ai_fused_op_) {
+        if (ai_fused_op_ && !par_) {
           // alpha = v_j^T OP v_j and ||OP v_j||^2 from the SpMV epilogue must agree with the CGS sweep
           const T da = std::fabs(hC()[2] - hA()[ai_j_ - 1]), dw = std::fabs(hC()[3] - hA()[ai_j_]);
           const T sc = std::sqrt(hA()[ai_j_]);

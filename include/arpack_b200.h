@@ -143,6 +143,11 @@ int ab200_register_csr_op_f64(const void* workl, int nrows, long long nnz, const
                               const double* val);
 int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
                               const float* val);
+/* The same under a communicator (p*aupd_c): nloc local rows of a row-partitioned matrix; columns >= nloc address
+ * halo_buf = [last halo_lo entries of the lower neighbour's x | first halo_hi of the upper neighbour's], filled by the
+ * library with an NCCL neighbour exchange before every product (PARPACK/EXAMPLES/MPI/pdsdrv1.f:463-483). */
+int ab200_register_csr_halo_op_f64(const void* workl, int comm, int nloc, long long nnz, const int* rowptr,
+                                   const int* col, const double* val, int halo_lo, int halo_hi, double* halo_buf);
 double ab200_fused_dot_maxdiff(const void* workl);
 /* per-kernel CUDA-event timing on the launching stream (bench.py's roofline): enable, run, read the table */
 void ab200_profile_enable(int on);

@@ -90,6 +90,37 @@ def test_parpack_semantics_differ_from_serial_as_in_the_reference(ab_comm, sym):
         assert np.abs(np.sort(par.dr[:nev]) - np.sort(opar.dr[:nev])).max() <= 1e-10 * np.abs(opar.dr).max()
 
 
+def test_registered_operator_under_a_communicator(ab_comm):
+    """ab200_register_csr_halo_op_f64: pdsaupd_c applies the (here halo-less, 1 rank) operator itself: one call per
+    solve, same counts and eigenvalues as the hand-off loop."""
+    ab, comm = ab_comm
+    A = ab.CsrOperator.laplace2d(41, 37)
+    r0 = np.random.default_rng(4).uniform(-1, 1, A.n)
+    a = ab.solve(A, A.n, 5, 20, "LA", tol=1e-10, mxiter=2000, resid=r0, comm=comm)
+    b = ab.solve(None, A.n, 5, 20, "LA", tol=1e-10, mxiter=2000, resid=r0, comm=comm, registered_op=A)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert b.nsteps == 0 and a.nsteps == int(a.iparam[8])
+    assert _counts(a) == _counts(b)
+    assert np.abs(a.d - b.d).max() <= 1e-10 * np.abs(a.d).max()
+    # a halo registration on the sequential entry point is refused loudly
+    with pytest.raises(ab.ArpackB200Error):
+        L = ab.lib()
+        w = None
+        import torch
+        halo = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+        def hijack():
+            res = ab.alloc_device_buffers(A.n, 20)
+            workl = np.zeros(20 * 20 + 8 * 20)
+            assert L.ab200_register_csr_halo_op_f64(workl.ctypes.data, comm, A.n, A.nnz, A.rowptr.data_ptr(),
+                                                    A.col.data_ptr(), A.val.data_ptr(), 0, 0, halo.data_ptr()) == 0
+            ido, info = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+            iparam, ipntr = np.zeros(11, dtype=np.int32), np.zeros(14, dtype=np.int32)
+            iparam[[0, 2, 3, 6]] = [1, 10, 1, 1]
+            ab.dsaupd_c(ido, "I", A.n, "LA", 5, 1e-10, res[2], 20, res[0], A.n, iparam, ipntr, res[1], workl, info)
+        hijack()
+
+
 def test_multi_gpu_check_under_torchrun_when_available():
     import torch
     ngpu = torch.cuda.device_count()

@@ -2,6 +2,7 @@
   1. PARPACK/TESTS/MPI/icb_parpack_c.c through pdsaupd_c/pdseupd_c: diag(1..1000) split over the ranks -> 992..1000
   2. 3-D 7-point Laplacian, z-slab partition with NCCL halo exchange, pdsaupd_c nev=6 ncv=24 'LA': eigenvalues and
      counts must equal the single-GPU dsaupd-free reference computed with scipy on rank 0 (dense-free: eigsh).
+  3. the same solve with the operator registered (ab200_register_csr_halo_op_f64): no hand-off, same counts.
 usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multigpu_check.py"""
 import os
 import sys
@@ -69,6 +70,15 @@ rn = torch.sqrt(rn).cpu().numpy()
 if rank == 0:
     print(f"[rank 0] global residuals: {rn}", flush=True)
 ok &= bool((rn < 1e-8).all())
+# ---- 3. the same solve with the operator registered (halo exchange + fused SpMV inside pdsaupd_c) ----
+reg = ab.solve(None, nloc, 6, 24, "LA", tol=1e-10, mxiter=2000, resid=r0, comm=comm, registered_op=A)
+same = (reg.info == 0 and reg.ierr == 0 and reg.nsteps == 0 and
+        (int(reg.iparam[2]), int(reg.iparam[4]), int(reg.iparam[8]), int(reg.iparam[10])) ==
+        (int(res.iparam[2]), int(res.iparam[4]), int(res.iparam[8]), int(res.iparam[10])) and
+        np.abs(np.sort(reg.d) - np.sort(res.d)).max() <= 1e-10 * np.abs(res.d).max())
+print(f"[rank {rank}] registered halo operator: info={reg.info} restarts={int(reg.iparam[2])} nopx={int(reg.iparam[8])} "
+      f"hand-offs={reg.nsteps} matches RCI={same}", flush=True)
+ok &= bool(same)
 st = ab.launch_stats()
 print(f"[rank {rank}] launches={st}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
