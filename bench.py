@@ -256,7 +256,8 @@ def run_ours(args):
     # ---- the opt-in registered-operator mode (one *aupd_c call per solve, K1+K2+K3 fused), reported beside the
     # strict-RCI headline; same operator, same restart budget, device-resident
     reg_mode = None
-    if not registered and not args.no_registered:
+    # (N = 1 only; for N > 1 run `bench.py --op-mode registered`, which times the registered mode in the main region)
+    if world == 1 and not registered and not args.no_registered:
         for _ in range(2):
             one_solve(reg=True)
         barrier()
