@@ -339,7 +339,9 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             else:
                 x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
                 y = workd[ipntr[1] - 1: ipntr[1] - 1 + n]
-                if mode >= 3 and bmat == "G" and i == 1:
+                if mode == 5:   # Cayley: the operator needs x and, at ido = 1, the M x the library provides
+                    op(x, y, workd[ipntr[2] - 1: ipntr[2] - 1 + n] if i == 1 else None)
+                elif mode >= 3 and bmat == "G" and i == 1:
                     op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], y, True)
                 else:
                     op(x, y)

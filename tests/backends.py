@@ -152,6 +152,10 @@ class Oracle:
                     y, ax = op(x)  # mode 2: op returns (M^-1 A x, A x); x is overwritten with A x
                     workd[ipntr[0] - 1: ipntr[0] - 1 + n] = ax
                     workd[ipntr[1] - 1: ipntr[1] - 1 + n] = y
+                elif mode == 5:
+                    # Cayley (dsaupd.f:128-140): y = inv(A - sigma M)(A + sigma M) x; at ido=1 M x is in workd(ipntr(3))
+                    bx = workd[ipntr[2] - 1: ipntr[2] - 1 + n] if ido.value == 1 else None
+                    workd[ipntr[1] - 1: ipntr[1] - 1 + n] = op(x, bx)
                 elif mode >= 3 and ido.value == 1 and bmat == "G":
                     workd[ipntr[1] - 1: ipntr[1] - 1 + n] = op(workd[ipntr[2] - 1: ipntr[2] - 1 + n], True)
                 else:

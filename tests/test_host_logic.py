@@ -372,3 +372,62 @@ def test_speculative_start_of_step_hits_and_changes_nothing(sym):
     # every step except the first of a sweep (and the start-vector product) can be speculated
     assert nopx - 2 * sweeps - 2 <= hits <= nopx
     assert hits > nopx // 2
+
+
+def _buckling_cayley_problem(n=80):
+    import scipy.sparse as sp
+    K = sp.diags([-np.ones(n - 1), 2.2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tocsc()            # SPD
+    KG = sp.diags([0.3 * np.ones(n - 1), np.linspace(-1.0, 2.0, n), 0.3 * np.ones(n - 1)], [-1, 0, 1]).tocsc()  # indefinite
+    M = sp.diags([np.ones(n - 1) / 6, 4 * np.ones(n) / 6, np.ones(n - 1) / 6], [-1, 0, 1]).tocsc()    # SPD
+    return K, KG, M
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostdouble"])
+def test_buckling_and_cayley_modes(backend):
+    """dsaupd modes 4 and 5 (dsaupd.f:118-140) and their back-transforms in dseupd (dseupd.f:672-712, 796-838):
+    lambda = sigma*theta/(theta-1) (buckling), lambda = sigma*(theta+1)/(theta-1) (Cayley), against dense solutions;
+    the product's host logic must follow the oracle count for count."""
+    import scipy.linalg as sl
+    import scipy.sparse.linalg as sla
+    n = 80
+    K, KG, M = _buckling_cayley_problem(n)
+    r0 = start(n, 6)
+    cls = Oracle if backend == "oracle" else HostDouble
+    # ---- mode 4: K x = lambda KG x, OP = inv(K - sigma KG) K, B = K ----
+    sigma = 0.6
+    lu = sla.splu((K - sigma * KG).tocsc())
+    lam = sl.eig(K.toarray(), KG.toarray(), right=False)
+    lam = np.sort(lam[np.isfinite(lam)].real)
+
+    def op4(x, is_bx=False):
+        return lu.solve(x if is_bx else K @ x)
+    r = cls().solve(op4, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=4, bmat="G", sigma=sigma, bop=lambda x: K @ x,
+                    resid=r0)
+    assert r.info == 0 and r.ierr == 0 and r.nconv == 4
+    near = lam[np.argsort(np.abs(lam - sigma))[:4]]
+    assert np.abs(np.sort(r.d) - np.sort(near)).max() < 1e-8
+    for k in range(4):  # K z = lambda KG z
+        assert np.linalg.norm(K @ r.z[k] - r.d[k] * (KG @ r.z[k])) < 1e-7 * np.linalg.norm(K @ r.z[k])
+    ref4 = r
+    # ---- mode 5: A x = lambda M x, OP = inv(A - sigma M)(A + sigma M), B = M ----
+    A = K
+    sigma5 = 1.5
+    lu5 = sla.splu((A - sigma5 * M).tocsc())
+    gev = np.sort(sl.eigh(A.toarray(), M.toarray(), eigvals_only=True))
+
+    def op5(x, bx):
+        return lu5.solve(A @ x + sigma5 * (bx if bx is not None else M @ x))
+    r = cls().solve(op5, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=5, bmat="G", sigma=sigma5, bop=lambda x: M @ x,
+                    resid=r0)
+    assert r.info == 0 and r.ierr == 0 and r.nconv == 4
+    near = gev[np.argsort(np.abs(gev - sigma5))[:4]]
+    assert np.abs(np.sort(r.d) - np.sort(near)).max() < 1e-8
+    for k in range(4):
+        assert np.linalg.norm(A @ r.z[k] - r.d[k] * (M @ r.z[k])) < 1e-7 * np.linalg.norm(A @ r.z[k])
+    if backend == "hostdouble":
+        o4 = Oracle().solve(op4, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=4, bmat="G", sigma=sigma,
+                            bop=lambda x: K @ x, resid=r0)
+        o5 = Oracle().solve(op5, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=5, bmat="G", sigma=sigma5,
+                            bop=lambda x: M @ x, resid=r0)
+        assert counts(ref4) == counts(o4) and counts(r) == counts(o5)
+        assert np.abs(ref4.d - o4.d).max() < 1e-10 and np.abs(r.d - o5.d).max() < 1e-10
