@@ -93,7 +93,7 @@ def test_symmetric_modes_vs_oracle(ab, case, host_buffers):
         bop, o_kw = (lambda x: A @ x), dict(mode=4, bmat="G", sigma=sigma)
         lam = sl.eig(A.toarray(), KG.toarray(), right=False)
         truth = np.sort(lam[np.isfinite(lam)].real)
-        want = truth[np.argsort(np.abs(truth - sigma))[:4]]
+        want = truth[np.argsort(-np.abs(truth / (truth - sigma)))[:4]]   # 'LM' in theta = lambda/(lambda-sigma)
     else:
         sigma = 1.5
         lu = sla.splu((A - sigma * M).tocsc())
@@ -101,7 +101,7 @@ def test_symmetric_modes_vs_oracle(ab, case, host_buffers):
         d_op = _dev(lambda x, bx=None: lu.solve(A @ x + sigma * (bx if bx is not None else M @ x)))
         bop, o_kw = (lambda x: M @ x), dict(mode=5, bmat="G", sigma=sigma)
         truth = np.sort(sl.eigh(A.toarray(), M.toarray(), eigvals_only=True))
-        want = truth[np.argsort(np.abs(truth - sigma))[:4]]
+        want = truth[np.argsort(-np.abs((truth + sigma) / (truth - sigma)))[:4]]   # 'LM' in the Cayley theta
     ref = Oracle().solve(o_op, n, 4, 16, "LM", bop=bop, c_abi_tol=True, **o_kw, **kw)
     got = ab.solve(d_op, n, 4, 16, "LM", bop=_dev(bop) if bop else None, host_buffers=host_buffers, **o_kw, **kw)
     assert ref.info == 0 and got.info == 0 and got.ierr == 0

@@ -404,7 +404,7 @@ def test_buckling_and_cayley_modes(backend):
     r = cls().solve(op4, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=4, bmat="G", sigma=sigma, bop=lambda x: K @ x,
                     resid=r0)
     assert r.info == 0 and r.ierr == 0 and r.nconv == 4
-    near = lam[np.argsort(np.abs(lam - sigma))[:4]]
+    near = lam[np.argsort(-np.abs(lam / (lam - sigma)))[:4]]          # 'LM' in theta = lambda/(lambda-sigma)
     assert np.abs(np.sort(r.d) - np.sort(near)).max() < 1e-8
     for k in range(4):  # K z = lambda KG z
         assert np.linalg.norm(K @ r.z[k] - r.d[k] * (KG @ r.z[k])) < 1e-7 * np.linalg.norm(K @ r.z[k])
@@ -420,7 +420,7 @@ def test_buckling_and_cayley_modes(backend):
     r = cls().solve(op5, n, 4, 16, "LM", tol=1e-12, mxiter=500, mode=5, bmat="G", sigma=sigma5, bop=lambda x: M @ x,
                     resid=r0)
     assert r.info == 0 and r.ierr == 0 and r.nconv == 4
-    near = gev[np.argsort(np.abs(gev - sigma5))[:4]]
+    near = gev[np.argsort(-np.abs((gev + sigma5) / (gev - sigma5)))[:4]]   # 'LM' in the Cayley theta
     assert np.abs(np.sort(r.d) - np.sort(near)).max() < 1e-8
     for k in range(4):
         assert np.linalg.norm(A @ r.z[k] - r.d[k] * (M @ r.z[k])) < 1e-7 * np.linalg.norm(A @ r.z[k])
