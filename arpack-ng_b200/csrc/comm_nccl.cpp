@@ -327,6 +327,11 @@ void ab200_comm_destroy(int handle) {
   c->comm = nullptr;
 }
 
+// 1 when the small all-reduces of this communicator go through peer memory, 0 when they use NCCL
+int ab200_comm_uses_p2p(int handle) {
+  ab200::NcclComm* c = ab200::comm_from_handle(handle);
+  return (c && c->p2p) ? 1 : 0;
+}
 int ab200_comm_rank(int handle) {
   ab200::NcclComm* c = ab200::comm_from_handle(handle);
   return c ? c->rank : -1;

@@ -359,7 +359,8 @@ def run_ours(args):
            "gpu_launches": st1["kernels"] - st0["kernels"], "allreduces": st1["allreduces"] - st0["allreduces"],
            "kernel_path": {"tma": st1["tma_path"] - st0["tma_path"], "generic": st1["generic_path"] - st0["generic_path"]},
            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-           "op_mode": "registered" if registered else "rci", "registered_op_mode": reg_mode}
+           "op_mode": "registered" if registered else "rci", "registered_op_mode": reg_mode,
+           "allreduce_path": (None if comm is None else ("peer-memory kernel" if L.ab200_comm_uses_p2p(comm) else "nccl"))}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -169,6 +169,9 @@ int ab200_nccl_unique_id(void* out128);                        /* rank 0: 128-by
 int ab200_comm_create(const void* id128, int rank, int nranks); /* collective; returns the comm handle (>= 1) */
 void ab200_comm_destroy(int handle);
 int ab200_comm_rank(int handle);
+/* 1 when the per-step all-reduces of this communicator run through peer memory (CUDA IPC over NVLink: one small kernel
+ * per all-reduce, sums in rank order), 0 when they use ncclAllReduce (IPC unavailable, > 8 ranks, AB200_P2P=0) */
+int ab200_comm_uses_p2p(int handle);
 int ab200_comm_size(int handle);
 
 /* ---- driver layer: the user's OP for the arpackmm-style tool (EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:806-841

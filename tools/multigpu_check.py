@@ -80,7 +80,8 @@ print(f"[rank {rank}] registered halo operator: info={reg.info} restarts={int(re
       f"hand-offs={reg.nsteps} matches RCI={same}", flush=True)
 ok &= bool(same)
 st = ab.launch_stats()
-print(f"[rank {rank}] launches={st}", flush=True)
+print(f"[rank {rank}] launches={st} all-reduce path="
+      f"{'peer-memory kernel' if ab.lib().ab200_comm_uses_p2p(comm) else 'nccl'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
