@@ -318,3 +318,21 @@ def test_registration_is_one_shot(ab):
     assert L.ab200_register_csr_op_f64(w.ctypes.data, A.n, A.nnz, A.rowptr.data_ptr(), A.col.data_ptr(),
                                        A.val.data_ptr()) == 0
     assert L.ab200_register_csr_op_f64(w.ctypes.data, 0, 0, None, None, None) == 0
+
+
+# --------------------------------------------------------------------------------------------------
+# committed golden vectors made by an independent implementation (SciPy's C translation of ARPACK-NG)
+# --------------------------------------------------------------------------------------------------
+import golden_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("registered", [False, True])
+@pytest.mark.parametrize("c", golden_cases.load(), ids=golden_cases.case_id)
+def test_cuda_path_reproduces_committed_scipy_arpack_vectors(ab, c, registered):
+    """tests/golden/scipy_arpack_cases.json: same start vector -> same nconv, restart count, OP*x count and
+    eigenvalues (1e-10) as SciPy's _arpacklib, through the C-ABI on the device (hand-off loop and registered operator)."""
+    S = golden_cases.PROBLEMS[c["problem"]]()
+    A = ab.CsrOperator.from_scipy(S)
+    r = ab.solve(None if registered else A, A.n, c["nev"], c["ncv"], c["which"], sym=c["sym"], tol=c["tol"],
+                 mxiter=3000, resid=golden_cases.start_vector(c, A.n), registered_op=A if registered else None)
+    golden_cases.check_against_golden(c, r, c["nev"])

@@ -431,3 +431,16 @@ def test_buckling_and_cayley_modes(backend):
                             bop=lambda x: M @ x, resid=r0)
         assert counts(ref4) == counts(o4) and counts(r) == counts(o5)
         assert np.abs(ref4.d - o4.d).max() < 1e-10 and np.abs(r.d - o5.d).max() < 1e-10
+
+
+import golden_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("c", golden_cases.load(), ids=golden_cases.case_id)
+def test_host_logic_reproduces_committed_scipy_arpack_vectors(c):
+    """The product's control code (over the test double) against golden vectors made by a third implementation."""
+    A = golden_cases.PROBLEMS[c["problem"]]()
+    n = A.shape[0]
+    r = HostDouble().solve(lambda x: A @ x, n, c["nev"], c["ncv"], c["which"], sym=c["sym"], tol=c["tol"], mxiter=3000,
+                           resid=golden_cases.start_vector(c, n))
+    golden_cases.check_against_golden(c, r, c["nev"])

@@ -323,3 +323,16 @@ def test_oracle_follows_scipy_arpack_translation_larger_and_float():
     b = Oracle().solve(lambda x: A32 @ x, n, 4, 16, "LA", tol=1e-4, mxiter=3000, resid=r0, dtype=np.float32)
     assert s["nconv"] == int(b.nconv) == 4
     assert np.abs(np.sort(s["vals"]) - np.sort(b.d)).max() < 1e-4 * np.abs(b.d).max()
+
+
+# ---- committed golden vectors from SciPy's ARPACK translation (tests/golden/scipy_arpack_cases.json) ----
+import golden_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("c", golden_cases.load(), ids=golden_cases.case_id)
+def test_oracle_reproduces_committed_scipy_arpack_vectors(c):
+    A = golden_cases.PROBLEMS[c["problem"]]()
+    n = A.shape[0]
+    r = Oracle().solve(lambda x: A @ x, n, c["nev"], c["ncv"], c["which"], sym=c["sym"], tol=c["tol"], mxiter=3000,
+                       resid=golden_cases.start_vector(c, n))
+    golden_cases.check_against_golden(c, r, c["nev"])
