@@ -354,6 +354,7 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
                  nconv=int(iparam[4]), nsteps=nsteps, workd=workd,
                  fused_dot_maxdiff=(L.ab200_fused_dot_maxdiff(workl.ctypes.data) if registered_op is not None else None))
     if info[0] < 0 or not eupd:
+        L.ab200_release(workl.ctypes.data)   # no *eupd will follow: drop the solve's context (and its HBM mirrors)
         return out
     select = np.zeros(ncv, dtype=np.int32)
     ierr = np.zeros(1, dtype=np.int32)
