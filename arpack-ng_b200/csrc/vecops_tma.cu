@@ -9,6 +9,8 @@
 //   UPD_SPEC  r = w - V*h ; ||r||^2 ; s[c] = sum_i V[i,c]*r[i]  (K7+K8 and, speculatively, the K9 dots:
 //             the tile is still in shared memory when r is known, so DGKS costs no extra pass over V)
 //   UPD       r -= V*s ; ||r||^2, predicated on the reference's test rnorm <= 0.717*wnorm (K9+K10)
+//             (both in two forms: k_upd, rows per lane, for j <= 32 and all UPD launches; k_orth, a column per
+//             warp, for UPD_SPEC beyond 32 columns -- see launch_upd)
 //   VQ        out(:,0:kout) = V(:,0:kin)*Q, optionally r = sigma*r + beta*out(:,c), ||r||^2 (K12-K16, K20)
 //
 // so a Lanczos/Arnoldi step reads V_j three times instead of the reference's four and

@@ -444,3 +444,35 @@ def test_host_logic_reproduces_committed_scipy_arpack_vectors(c):
     r = HostDouble().solve(lambda x: A @ x, n, c["nev"], c["ncv"], c["which"], sym=c["sym"], tol=c["tol"], mxiter=3000,
                            resid=golden_cases.start_vector(c, n))
     golden_cases.check_against_golden(c, r, c["nev"])
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+def test_nonsym_complex_shift_real_and_imaginary_part_modes(mode):
+    """dnaupd modes 3 and 4 with a complex shift (dnaupd.f:119-143, EXAMPLES/NONSYM/dndrv4.f style): OP is the real
+    (mode 3) or imaginary (mode 4) part of inv(A - sigma I); dneupd leaves the Ritz values of OP untransformed
+    (type REALPT / IMAGPT, dneupd.f:950-991) and the caller recovers lambda by Rayleigh quotients (remark 3)."""
+    n = 60
+    A = np.diag(2.0 + 0.05 * np.arange(n)) + np.diag(-1.3 * np.ones(n - 1), -1) + np.diag(0.7 * np.ones(n - 1), 1) \
+        + np.diag(0.4 * np.ones(n - 3), 3)
+    sigma = 2.5 + 0.8j
+    S = np.linalg.inv(A - sigma * np.eye(n))
+    op = (lambda x: (S @ x).real) if mode == 3 else (lambda x: (S @ x).imag)
+    r0 = start(n, 9)
+    kw = dict(sym=False, tol=1e-9, mxiter=3000, mode=mode, bmat="I", sigma=sigma.real, sigmai=sigma.imag, resid=r0)
+    a = HostDouble().solve(op, n, 4, 24, "LM", **kw)
+    b = Oracle().solve(op, n, 4, 24, "LM", **kw)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert counts(a) == counts(b)
+    assert np.abs(a.dr[:a.nconv] - b.dr[:b.nconv]).max() < 1e-8 and np.abs(a.di[:a.nconv] - b.di[:b.nconv]).max() < 1e-8
+    # Rayleigh quotients of the returned vectors are eigenvalues of A (the ones that dominate OP's spectrum)
+    ev = np.linalg.eigvals(A)
+    k = 0
+    while k < a.nconv:
+        if a.di[k] != 0 and k + 1 < a.nconv + 1:
+            x = a.z[k] + 1j * a.z[k + 1]
+            k += 2
+        else:
+            x = a.z[k].astype(complex)
+            k += 1
+        lam = (x.conj() @ (A @ x)) / (x.conj() @ x)
+        assert np.abs(ev - lam).min() < 1e-6 or np.abs(ev - np.conj(lam)).min() < 1e-6
