@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(kP2pMaxCount) k_p2p_allreduce(T* mb, int count
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
       if (got >= seq) break;
-      if (clock64() - t0 > 6000000000LL) __trap();  // a peer never arrived (~3 s): fail loudly instead of hanging
+      // a peer never arrived: fail loudly instead of hanging.  The bound (~60 s) is far above any start-up skew
+      // between ranks (module loading, allocations), which an MPI or NCCL collective would simply wait out.
+      if (clock64() - t0 > 120000000000LL) __trap();
     } while (true);
   }
   __syncthreads();
