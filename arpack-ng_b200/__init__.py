@@ -287,7 +287,7 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             info[0] = 1
     if registered_op is not None:
         # opt-in extension: the library applies the CSR operator itself (one *aupd call per solve)
-        if registered_op.val.dtype != t_dt:
+        if registered_op.val.dtype not in (t_dt, np_dt):
             raise ArpackB200Error("registered_op values must have the solve's dtype")
         if comm is not None:
             # row-partitioned operator: the library also runs the neighbour exchange of the halo planes
@@ -303,8 +303,9 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
                                                   registered_op.halo_hi, registered_op.halo.data_ptr())
         else:
             reg = L.ab200_register_csr_op_f64 if np_dt == np.float64 else L.ab200_register_csr_op_f32
-            rc = reg(workl.ctypes.data, registered_op.n, registered_op.nnz, registered_op.rowptr.data_ptr(),
-                     registered_op.col.data_ptr(), registered_op.val.data_ptr())
+            # device tensors are used in place; host arrays (HostCsr) are uploaded once by the library at ido = 0
+            rc = reg(workl.ctypes.data, registered_op.n, registered_op.nnz, _addr(registered_op.rowptr),
+                     _addr(registered_op.col), _addr(registered_op.val))
         if rc != 0:
             raise ArpackB200Error("register_csr_op failed")
         if op is None:
@@ -501,6 +502,28 @@ class CsrOperator:
         if rc != 0:
             raise ArpackB200Error("residuals failed")
         return out
+
+
+class HostCsr:
+    """A CSR matrix in HOST memory (int32 indices), as a caller of the reference owns it (arpackSolver.hpp:361-424 reads
+    the matrix into host memory).  Pass it as ``solve(None, ..., registered_op=HostCsr(...), host_buffers=True)``: the
+    library uploads it once and runs the whole solve on the GPU."""
+
+    def __init__(self, n, rowptr, col, val):
+        self.n, self.rowptr, self.col, self.val = int(n), rowptr, col, val
+        self.nnz = int(val.shape[0])
+
+    @staticmethod
+    def from_operator(A, pinned=True):
+        """Host copy of a CsrOperator (pinned by default, like alloc_host_buffers)."""
+        def _h(t):
+            t = t.cpu()
+            return t.pin_memory() if pinned else t
+        return HostCsr(A.n, _h(A.rowptr), _h(A.col), _h(A.val))
+
+    def nbytes(self):
+        return sum(int(a.numel() * a.element_size()) if hasattr(a, "numel") else int(a.nbytes)
+                   for a in (self.rowptr, self.col, self.val))
 
 
 def hashed_start_vector(n, i0=0, seed=0x5EED, device="cuda"):

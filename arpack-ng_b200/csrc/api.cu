@@ -70,6 +70,7 @@ struct Ctx {
   T *resid_d = nullptr, *v_d = nullptr, *workd_d = nullptr;
   int64_t ldv_d = 0;
   T* z_mirror = nullptr;
+  void* csr_mirror[3] = {nullptr, nullptr, nullptr};  // HBM copies of a registered operator given as host arrays
   int last_ido = 0;
   int last_ipntr[3] = {0, 0, 0};
   bool finished = false;
@@ -82,6 +83,8 @@ struct Ctx {
       if (workd_host) ops->release(workd_d);
       ops->release(z_mirror);
     }
+    for (void* p : csr_mirror)
+      if (p) cudaFree(p);
   }
 };
 
@@ -163,6 +166,18 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
   if ((d.comm != 0) != c->par) throw CudaError("registered CSR operator: halo registration needs the p*aupd_c entry "
                                                "points (and plain registration the sequential ones)");
   CudaVecOps<T>* ops = c->ops.get();
+  // a caller that owns its matrix on the host (arpackSolver.hpp reads A into host memory, :361-424) registers those
+  // arrays as they are: they are copied to HBM once, here, and the copies live as long as the solve's context
+  auto stage = [&](const void* host, size_t bytes, int slot) -> const void* {
+    if (ops->is_device_pointer(host)) return host;
+    if (d.comm != 0) throw CudaError("registered CSR operator: the halo variant takes device arrays");
+    AB200_CUDA_CHECK(cudaMalloc(&c->csr_mirror[slot], bytes));
+    AB200_CUDA_CHECK(cudaMemcpyAsync(c->csr_mirror[slot], host, bytes, cudaMemcpyHostToDevice, ops->stream()));
+    return c->csr_mirror[slot];
+  };
+  d.rowptr = static_cast<const int*>(stage(d.rowptr, sizeof(int) * ((size_t)d.nrows + 1), 0));
+  d.col = static_cast<const int*>(stage(d.col, sizeof(int) * (size_t)d.nnz, 1));
+  d.val = static_cast<const T*>(stage(d.val, sizeof(T) * (size_t)d.nnz, 2));
   solver->set_registered_op(
       [d](const T* x, T* y) {
         if (csr_op_apply<T>(d, x, y) != 0) throw CudaError("registered CSR operator: SpMV launch failed");

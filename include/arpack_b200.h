@@ -138,7 +138,11 @@ void ab200_reset_seed(void);
  * -- the loop of EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:787-846 without a host round trip per step.  K1+K2 are folded
  * into the SpMV and alpha = v^T OP v, ||OP v||^2 come out of its epilogue.  The registration is ONE-SHOT: it is consumed
  * by the next ido = 0 call with this workl (and dropped there if the solve is not mode 1 / bmat 'I' / sequential), so a
- * later solve that happens to reuse the address runs the plain protocol.  nrows = 0 unregisters. */
+ * later solve that happens to reuse the address runs the plain protocol.  nrows = 0 unregisters.
+ * rowptr/col/val may each be DEVICE arrays (used in place, must outlive the solve) or HOST arrays (copied to HBM once at
+ * ido = 0 and owned by the solve's context; they must stay valid until that call): a caller whose matrix, resid, v and
+ * workd all live in host memory -- every caller of the reference -- runs the whole solve on the GPU with one upload of
+ * the matrix and one download of V/resid, instead of four PCIe crossings of n values per Lanczos step. */
 int ab200_register_csr_op_f64(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,
                               const double* val);
 int ab200_register_csr_op_f32(const void* workl, int nrows, long long nnz, const int* rowptr, const int* col,

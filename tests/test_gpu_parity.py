@@ -296,6 +296,29 @@ def test_registered_csr_operator_matches_rci_and_oracle(ab, case):
         assert np.abs(np.sort(b.dr[:nev]) - np.sort(ref.dr[:nev])).max() <= rtol * np.abs(ref.dr).max()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_registered_host_csr_with_host_buffers_matches_device_path(ab, pinned):
+    """A caller that owns EVERYTHING on the host (CSR matrix, resid, V, workd -- every caller of the reference) registers
+    its host matrix: the library uploads it once, one dsaupd_c call runs the solve, V/resid come back at ido = 99 and
+    dseupd_c works on the host arrays.  Same path (counts) and eigenvalues as the device-resident registered solve."""
+    A = ab.CsrOperator.laplace2d(300, 260)
+    n, nev, ncv = A.n, 6, 24
+    r0 = np.random.default_rng(11).uniform(-1, 1, n)
+    dev = ab.solve(None, n, nev, ncv, "LA", tol=1e-10, mxiter=3000, resid=r0, registered_op=A)
+    H = ab.HostCsr.from_operator(A, pinned=pinned)
+    hst = ab.solve(None, n, nev, ncv, "LA", tol=1e-10, mxiter=3000, resid=r0, registered_op=H, host_buffers=True,
+                   pinned=pinned)
+    assert dev.info == hst.info == 0 and dev.ierr == hst.ierr == 0
+    assert hst.nsteps == 0                                  # never handed an OP*x back
+    assert _counts(dev) == _counts(hst)
+    assert np.abs(dev.d - hst.d).max() <= RTOL64 * np.abs(dev.d).max()
+    # the eigenvectors arrived in the caller's HOST array: check A z = lambda z there
+    S = A.to_scipy()
+    Z = np.asarray(hst.z).reshape(ncv, n)[:nev].T
+    res = np.linalg.norm(S @ Z - Z * hst.d[None, :], axis=0)
+    assert (res <= 1e-8 * 8.0).all(), res
+
+
 def test_registered_operator_row_count_mismatch_fails_loudly(ab):
     A = ab.CsrOperator.laplace2d(20, 20)
     with pytest.raises(ab.ArpackB200Error):   # info = -9990 from the C-ABI, surfaced by the binding
