@@ -12,5 +12,7 @@ struct ref_ctx {
   /* SAVE'd locals of every routine, one block per precision, allocated lazily */
   void* dstate;
   void* sstate;
+  void* zstate; /* complex paths (ref_impl_complex.inc) */
+  void* cstate;
 };
 #endif

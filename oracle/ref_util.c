@@ -15,6 +15,8 @@ void ref_ctx_free(ref_ctx* c) {
   if (!c) return;
   free(c->dstate);
   free(c->sstate);
+  free(c->zstate);
+  free(c->cstate);
   free(c);
 }
 void ref_ctx_set_comm(ref_ctx* c, int rank, int nranks, ref_allreduce_fn fn, void* user) {

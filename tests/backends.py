@@ -50,6 +50,17 @@ def lib():
                           C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
                           C.c_int, c_int_p]
             f.restype = None
+        for p, rp, rt in (("z", c_dbl_p, C.c_double), ("c", c_flt_p, C.c_float)):
+            vp = C.c_void_p
+            f = getattr(L, f"ref_{p}naupd")
+            f.argtypes = [C.c_void_p, c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rp, vp, C.c_int, vp, C.c_int,
+                          c_int_p, c_int_p, vp, vp, C.c_int, rp, c_int_p]
+            f.restype = None
+            f = getattr(L, f"ref_{p}neupd_ri")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, vp, vp, C.c_int, rt, rt, vp, C.c_char_p, C.c_int,
+                          C.c_char_p, C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p, c_int_p, vp, vp, C.c_int, rp,
+                          c_int_p]
+            f.restype = None
         L.ref_dlarnv2.argtypes = [c_int_p, C.c_int, c_dbl_p]
         L.ref_csr_spmv.argtypes = [C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int]
         L.ref_set_blas_threads.argtypes = [C.c_int]
@@ -195,6 +206,75 @@ class Oracle:
             out.update(dr=dr, di=di, z=z, ierr=ierr.value)
         out.update(workl_eupd=workl.copy(), v_eupd=v.copy(), ipntr_eupd=ipntr.copy(), select=select.copy())
         return out
+
+
+def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
+                   dtype=np.complex128, bop=None, rvec=True, sigma=0.0, c_abi_tol=False, ishift=1, eupd=True, ldv=None):
+    """RCI loop around znaupd/zneupd (cnaupd/cneupd for complex64) as EXAMPLES/COMPLEX/zndrv1.f drives it.
+    op(x)->y, bop(x)->y; mode 3 with bmat='G': op(x, bx) receives workd(ipntr(3)) = B x as second argument."""
+    dt = np.dtype(dtype)
+    p = "z" if dt == np.complex128 else "c"
+    rdt = np.float64 if p == "z" else np.float32
+    rp = c_dbl_p if p == "z" else c_flt_p
+    rt = C.c_double if p == "z" else C.c_float
+    ldv = ldv or n
+    lworkl = 3 * ncv * ncv + 5 * ncv
+    v = np.zeros((ncv, ldv), dtype=dt)
+    workd = np.zeros(3 * n, dtype=dt)
+    workl = np.zeros(lworkl, dtype=dt)
+    rwork = np.zeros(ncv, dtype=rdt)
+    iparam = np.zeros(11, dtype=np.int32)
+    ipntr = np.zeros(14, dtype=np.int32)
+    iparam[0], iparam[2], iparam[3], iparam[6] = ishift, mxiter, 1, mode
+    info = C.c_int(0)
+    if resid is None:
+        res = np.zeros(n, dtype=dt)
+    else:
+        res = np.array(resid, dtype=dt).copy()
+        info.value = 1
+    ido = C.c_int(0)
+    tolv = rt(tol)
+    aupd = self._fn(f"{p}naupd")
+    nsteps = 0
+    vp = lambda a: a.ctypes.data  # noqa: E731
+    while True:
+        if c_abi_tol:
+            tolv = rt(tol)
+        aupd(*self._ctxargs(p), C.byref(ido), bmat.encode(), n, which.encode(), nev, C.byref(tolv), vp(res), ncv, vp(v),
+             ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), vp(workd), vp(workl), lworkl, _p(rwork, rp), C.byref(info))
+        if ido.value in (-1, 1):
+            x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
+            if mode == 3 and bmat == "G":
+                bx = workd[ipntr[2] - 1: ipntr[2] - 1 + n] if ido.value == 1 else None
+                workd[ipntr[1] - 1: ipntr[1] - 1 + n] = op(x, bx)
+            else:
+                workd[ipntr[1] - 1: ipntr[1] - 1 + n] = op(x)
+            nsteps += 1
+        elif ido.value == 2:
+            workd[ipntr[1] - 1: ipntr[1] - 1 + n] = bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n])
+        else:
+            break
+    out = Result(info=info.value, iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v.copy(),
+                 resid=res.copy(), nconv=int(iparam[4]), tol_eff=tolv.value, nsteps=nsteps)
+    if info.value < 0 or not eupd:
+        return out
+    select = np.zeros(ncv, dtype=np.int32)
+    ierr = C.c_int(0)
+    tol_e = tol if c_abi_tol else tolv.value
+    d = np.zeros(nev + 1, dtype=dt)
+    z = np.zeros((nev, n), dtype=dt)
+    workev = np.zeros(2 * ncv, dtype=dt)
+    sg = complex(sigma)
+    self._fn(f"{p}neupd_ri")(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), vp(d), vp(z), n, rt(sg.real),
+                             rt(sg.imag), vp(workev), bmat.encode(), n, which.encode(), nev, rt(tol_e), vp(res), ncv,
+                             vp(v), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), vp(workd), vp(workl), lworkl,
+                             _p(rwork, rp), C.byref(ierr))
+    out.update(d=d[:nev], z=z, ierr=ierr.value, workl_eupd=workl.copy(), v_eupd=v.copy(), ipntr_eupd=ipntr.copy(),
+               select=select.copy())
+    return out
+
+
+Oracle.solve_complex = _solve_complex
 
 
 # ----------------------------------------------------------------------------------------------------
