@@ -289,13 +289,14 @@ def build_hostdouble():
     import scipy
     os.makedirs(os.path.dirname(_HD_SO), exist_ok=True)
     src = os.path.join(_ROOT, "tests", "hostdouble", "hostdouble.cpp")
-    deps = [src] + glob.glob(os.path.join(_ROOT, "arpack-ng_b200", "csrc", "*.hpp"))
+    src_z = os.path.join(_ROOT, "tests", "hostdouble", "hostdouble_cplx.cpp")
+    deps = [src, src_z] + glob.glob(os.path.join(_ROOT, "arpack-ng_b200", "csrc", "*.hpp"))
     if os.path.exists(_HD_SO) and all(os.path.getmtime(_HD_SO) >= os.path.getmtime(d) for d in deps):
         return
     blas = os.path.abspath(glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs",
                                                   "libscipy_openblas*.so"))[0])
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _HD_SO, src, blas,
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _HD_SO, src, src_z, blas,
                            "-Wl,-rpath," + os.path.dirname(blas)])
 
 
@@ -329,6 +330,21 @@ def hostdouble_lib():
                           C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
                           C.c_int, c_int_p]
             f.restype = None
+        L.hdz_new.restype = C.c_void_p
+        L.hdz_new.argtypes = [C.c_int]
+        L.hdz_free.argtypes = [C.c_void_p, C.c_int]
+        L.hdz_stats.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        for p, rp, rt in (("z", c_dbl_p, C.c_double), ("c", c_flt_p, C.c_float)):
+            vp = C.c_void_p
+            f = getattr(L, f"hd_{p}naupd")
+            f.argtypes = [C.c_void_p, c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rp, vp, C.c_int, vp, C.c_int,
+                          c_int_p, c_int_p, vp, vp, C.c_int, rp, c_int_p]
+            f.restype = None
+            f = getattr(L, f"hd_{p}neupd_ri")
+            f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_int_p, vp, vp, C.c_int, rt, rt, vp, C.c_char_p, C.c_int,
+                          C.c_char_p, C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p, c_int_p, vp, vp, C.c_int, rp,
+                          c_int_p]
+            f.restype = None
         _hd = L
     return _hd
 
@@ -343,6 +359,7 @@ class HostDouble(Oracle):
     def __init__(self, rank=None, nranks=None, allreduce=None):
         self.L = hostdouble_lib()
         self._procs = {True: C.c_void_p(self.L.hd_new(1)), False: C.c_void_p(self.L.hd_new(0))}
+        self._procs_z = {True: C.c_void_p(self.L.hdz_new(1)), False: C.c_void_p(self.L.hdz_new(0))}
         self._cb = None
         if rank is not None:
             self._cb = _make_allreduce_cb(allreduce)
@@ -353,10 +370,14 @@ class HostDouble(Oracle):
         try:
             for isd, pr in self._procs.items():
                 self.L.hd_free(pr, int(isd))
+            for isd, pr in self._procs_z.items():
+                self.L.hdz_free(pr, int(isd))
         except Exception:
             pass
 
     def _ctxargs(self, p):
+        if p in ("z", "c"):
+            return (self._procs_z[p == "z"],)
         return (self._procs[p == "d"],)
 
     def register_op(self, op, n, dtype=np.float64, fused=False):
