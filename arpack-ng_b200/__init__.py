@@ -81,6 +81,16 @@ def lib():
             f = getattr(L, f"{pre}{p}neupd_c")
             f.argtypes = _sig_neupd(vp, rt, par)
             f.restype = None
+    for p, rt in (("z", C.c_double), ("c", C.c_float)):
+        rp = C.POINTER(rt)
+        f = getattr(L, f"{p}naupd_c")   # ICB/arpack.h:10,20
+        f.argtypes = [c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p, c_int_p,
+                      vp, vp, C.c_int, rp, c_int_p]
+        f.restype = None
+        f = getattr(L, f"ab200_{p}neupd_ri")   # [cz]neupd_c with sigma as two reals (ctypes has no C complex)
+        f.argtypes = [C.c_int, C.c_char_p, c_int_p, vp, vp, C.c_int, rt, rt, vp, C.c_char_p, C.c_int, C.c_char_p,
+                      C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p, c_int_p, vp, vp, C.c_int, rp, c_int_p]
+        f.restype = None
     L.ab200_set_stream.argtypes = [vp]
     L.ab200_get_stream.restype = vp
     L.ab200_set_kernel_mode.argtypes = [C.c_int]
@@ -372,6 +382,83 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
                  iparam, ipntr, workd, workl, ierr, comm=comm)
         out.update(dr=dr, di=di, z=v, ierr=int(ierr[0]))
     out.update(workl_eupd=workl.copy(), ipntr_eupd=ipntr.copy())
+    L.ab200_release(workl.ctypes.data)
+    return out
+
+
+def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.complex128,
+                  bop=None, rvec=True, sigma=0.0, device="cuda", host_buffers=False, ishift=1, eupd=True):
+    """znaupd_c/zneupd_c (cnaupd_c/cneupd_c for complex64) solve through the C-ABI, the loop of
+    EXAMPLES/COMPLEX/zndrv1.f.  Device arrays (default): ``op(x, y)`` gets complex CUDA tensor views of the workd slots;
+    host_buffers=True: numpy views.  Mode 3 with bmat='G': ``op(x, y, bx)`` also receives workd(ipntr(3)) at ido = 1."""
+    import torch
+    L = lib()
+    np_dt = np.dtype(dtype)
+    p_, rt = ("z", C.c_double) if np_dt == np.complex128 else ("c", C.c_float)
+    r_dt = np.float64 if p_ == "z" else np.float32
+    t_dt = torch.complex128 if p_ == "z" else torch.complex64
+    lworkl = 3 * ncv * ncv + 5 * ncv
+    workl = np.zeros(lworkl, dtype=np_dt)
+    rwork = np.zeros(ncv, dtype=r_dt)
+    iparam = np.zeros(11, dtype=np.int32)
+    ipntr = np.zeros(14, dtype=np.int32)
+    iparam[0], iparam[2], iparam[3], iparam[6] = ishift, mxiter, 1, mode
+    ido = np.zeros(1, dtype=np.int32)
+    info = np.zeros(1, dtype=np.int32)
+    ldv = n
+    if host_buffers:
+        v, workd, res = np.zeros(n * ncv, dtype=np_dt), np.zeros(3 * n, dtype=np_dt), np.zeros(n, dtype=np_dt)
+        if resid is not None:
+            res[:] = np.asarray(resid, dtype=np_dt)
+            info[0] = 1
+    else:
+        v = torch.zeros(n * ncv, dtype=t_dt, device=device)
+        workd = torch.zeros(3 * n, dtype=t_dt, device=device)
+        res = torch.zeros(n, dtype=t_dt, device=device)
+        if resid is not None:
+            res.copy_(torch.as_tensor(np.asarray(resid, dtype=np_dt)))
+            info[0] = 1
+    f_aupd = getattr(L, f"{p_}naupd_c")
+    rwp = rwork.ctypes.data_as(C.POINTER(rt))
+    cargs = (ido.ctypes.data_as(c_int_p), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(res), ncv, _addr(v), ldv,
+             iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
+             info.ctypes.data_as(c_int_p))
+    nsteps = 0
+    while True:
+        f_aupd(*cargs)
+        if info[0] == INFO_DEVICE_ERROR:
+            raise ArpackB200Error("naupd_c (complex): CUDA device error (see stderr); there is no CPU fallback")
+        i = ido[0]
+        if i == 1 or i == -1:
+            x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
+            y = workd[ipntr[1] - 1: ipntr[1] - 1 + n]
+            if mode == 3 and bmat == "G":
+                op(x, y, workd[ipntr[2] - 1: ipntr[2] - 1 + n] if i == 1 else None)
+            else:
+                op(x, y)
+            nsteps += 1
+        elif i == 2:
+            bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n], workd[ipntr[1] - 1: ipntr[1] - 1 + n])
+        else:
+            break
+    out = Result(info=int(info[0]), iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v, resid=res,
+                 nconv=int(iparam[4]), nsteps=nsteps, workd=workd)
+    if info[0] < 0 or not eupd:
+        L.ab200_release(workl.ctypes.data)
+        return out
+    select = np.zeros(ncv, dtype=np.int32)
+    ierr = np.zeros(1, dtype=np.int32)
+    d = np.zeros(nev + 1, dtype=np_dt)
+    workev = np.zeros(2 * ncv, dtype=np_dt)
+    sg = complex(sigma)
+    getattr(L, f"ab200_{p_}neupd_ri")(int(rvec), b"A", select.ctypes.data_as(c_int_p), _addr(d), _addr(v), ldv,
+                                      rt(sg.real), rt(sg.imag), _addr(workev), bmat.encode(), n, which.encode(), nev,
+                                      rt(tol), _addr(res), ncv, _addr(v), ldv, iparam.ctypes.data_as(c_int_p),
+                                      ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
+                                      ierr.ctypes.data_as(c_int_p))
+    if ierr[0] == INFO_DEVICE_ERROR:
+        raise ArpackB200Error("neupd_c (complex): CUDA device error (see stderr)")
+    out.update(d=d[:nev], z=v, ierr=int(ierr[0]), workl_eupd=workl.copy(), ipntr_eupd=ipntr.copy())
     L.ab200_release(workl.ctypes.data)
     return out
 

@@ -31,6 +31,10 @@
 
 namespace ab200 {
 NcclComm* comm_from_handle(int handle);
+// complex entry points live in api_cplx.cu
+void release_cplx(const void* workl);
+void release_all_cplx();
+void reset_seed_cplx();
 
 namespace {
 
@@ -358,6 +362,8 @@ void neupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const 
 }
 
 }  // namespace
+
+void set_last_counters(const Counters& c) { g_last_counters = c; }  // COMMON /timing/ as seen by stat_c
 }  // namespace ab200
 
 using namespace ab200;
@@ -529,6 +535,7 @@ void ab200_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream;
 void* ab200_get_stream(void) { return (void*)g_stream; }
 void ab200_set_kernel_mode(int mode) { g_kernel_mode = mode; }
 void ab200_release(const void* workl) {
+  release_cplx(workl);
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().erase(workl);
   table<float>().erase(workl);
@@ -536,6 +543,7 @@ void ab200_release(const void* workl) {
   registered_ops<float>().erase(workl);
 }
 void ab200_release_all(void) {
+  release_all_cplx();
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().clear();
   table<float>().clear();
@@ -548,6 +556,7 @@ void ab200_reset_seed(void) {
   Globals<double>::seed = SeedState(); Globals<double>::seed_par = SeedState();
   Globals<float>::seed = SeedState(); Globals<float>::seed_par = SeedState();
   Globals<double>::smlnum_first = -1.0; Globals<float>::smlnum_first = -1.0f;
+  reset_seed_cplx();
 }
 // Registered-operator mode: y = A x for a square CSR matrix resident in HBM is applied by the
 // library itself for the solve keyed to `workl` (mode 1, bmat = 'I'), so *aupd_c never returns ido = +-1 and one call

@@ -27,6 +27,17 @@ extern "C" {
 
 typedef int a_int;  /* arpackdef.h.in:8-14 (LP64 build) */
 typedef int a_fint; /* MPI_Fint of ICB/parpack.h:7-8; here: handle from ab200_comm_create() */
+/* a_fcomplex / a_dcomplex of arpackdef.h.in:19-41 (`float _Complex` / `double _Complex`).  In C they are exactly
+ * those types; a C++ translation unit sees a two-member struct, which the SysV x86-64 and AArch64 ABIs lay out AND pass
+ * by value like the C99 complex types (ICB/arpack.hpp:213-216 relies on the same equivalence for std::complex). */
+#ifdef __cplusplus
+typedef struct { float re, im; } a_fcomplex;
+typedef struct { double re, im; } a_dcomplex;
+#else
+#include <complex.h>
+typedef float _Complex a_fcomplex;
+typedef double _Complex a_dcomplex;
+#endif
 
 /* ---- ICB/arpack.h:14-21 (bind(c) shims SRC/icbads.F90:3-92, icbadn.F90:3-97, icbass.F90, icbasn.F90) ---- */
 void dsaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, double* resid,
@@ -56,6 +67,42 @@ void sneupd_c(a_int rvec, char const* howmny, a_int const* select, float* dr, fl
               float sigmar, float sigmai, float* workev, char const* bmat, a_int n, char const* which, a_int nev,
               float tol, float* resid, a_int ncv, float* v, a_int ldv, a_int* iparam, a_int* ipntr, float* workd,
               float* workl, a_int lworkl, a_int* info);
+
+/* ---- complex Arnoldi: ICB/arpack.h:10-11,20-21 (bind(c) shims SRC/icbacn.F90, icbazn.F90:3-94 over SRC/cnaupd.f,
+ * cneupd.f, znaupd.f:384, zneupd.f:248).  workl holds 3*ncv^2 + 5*ncv complex entries, rwork ncv reals, d nev+1,
+ * workev 2*ncv; which is one of LM SM LR SR LI SI; modes 1-3.  resid, v, workd, z: host or device, as above. */
+void znaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, a_dcomplex* resid,
+              a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,
+              a_int lworkl, double* rwork, a_int* info);
+void zneupd_c(a_int rvec, char const* howmny, a_int const* select, a_dcomplex* d, a_dcomplex* z, a_int ldz,
+              a_dcomplex sigma, a_dcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
+              double tol, a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
+              a_dcomplex* workd, a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info);
+void cnaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, a_fcomplex* resid,
+              a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd, a_fcomplex* workl,
+              a_int lworkl, float* rwork, a_int* info);
+void cneupd_c(a_int rvec, char const* howmny, a_int const* select, a_fcomplex* d, a_fcomplex* z, a_int ldz,
+              a_fcomplex sigma, a_fcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+              a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd,
+              a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info);
+/* the same with sigma as two reals, for bindings that cannot pass a C complex by value (Python ctypes) */
+void ab200_zneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* d, void* z, a_int ldz, double sigma_re,
+                     double sigma_im, void* workev, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+                     void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr, void* workd, void* workl,
+                     a_int lworkl, double* rwork, a_int* info);
+void ab200_cneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* d, void* z, a_int ldz, float sigma_re,
+                     float sigma_im, void* workev, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+                     void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr, void* workd, void* workl,
+                     a_int lworkl, float* rwork, a_int* info);
+/* legacy Fortran ABI of the same (SRC/znaupd.f:384, zneupd.f:248) */
+void znaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, a_dcomplex* resid,
+             a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,
+             a_int* lworkl, double* rwork, a_int* info, size_t bmat_len, size_t which_len);
+void zneupd_(a_int* rvec, const char* howmny, a_int* select, a_dcomplex* d, a_dcomplex* z, a_int* ldz,
+             a_dcomplex* sigma, a_dcomplex* workev, const char* bmat, a_int* n, const char* which, a_int* nev,
+             double* tol, a_dcomplex* resid, a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr,
+             a_dcomplex* workd, a_dcomplex* workl, a_int* lworkl, double* rwork, a_int* info, size_t howmny_len,
+             size_t bmat_len, size_t which_len);
 
 /* ---- ICB/parpack.h:12-27 (PARPACK/SRC/MPI/icbpds.F90, icbpdn.F90, icbpss.F90, icbpsn.F90).
  * n is the LOCAL row count; all ranks call in lock-step.  MPI_ALLREDUCE of the reference

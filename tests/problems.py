@@ -56,3 +56,23 @@ def convdiff2d(nx, rho=100.0):
     A = (sp.kron(sp.eye(nx), T) + sp.kron(off, -sp.eye(nx) / h ** 2)).tocsr()
     A.sort_indices()
     return A
+
+
+def complex_tridiag(n, rho=10.0, imag_span=50.0):
+    """1-D convection-diffusion (EXAMPLES/COMPLEX/zndrv1.f:400-440 style: 2/h^2 on the diagonal, -1/h^2 -+ rho/(2h) off
+    it) with an imaginary ramp added to the diagonal so that the matrix and its spectrum are genuinely complex."""
+    h = 1.0 / (n + 1)
+    A = sp.diags([(-1 / h ** 2 - rho / 2 / h) * np.ones(n - 1),
+                  (2 / h ** 2 + 0j) * np.ones(n) + 1j * np.linspace(0, imag_span, n),
+                  (-1 / h ** 2 + rho / 2 / h) * np.ones(n - 1)], [-1, 0, 1]).tocsr().astype(np.complex128)
+    A.sort_indices()
+    return A
+
+
+def complex_convdiff2d(nx, rho=10.0, imag_span=200.0):
+    """The dndrv1-style 2-D operator plus i*diag(ramp): non-Hermitian, complex spectrum."""
+    A = convdiff2d(nx, rho).astype(np.complex128)
+    n = nx * nx
+    A = (A + sp.diags([1j * np.linspace(0, imag_span, n)], [0])).tocsr()
+    A.sort_indices()
+    return A

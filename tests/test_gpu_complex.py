@@ -1,0 +1,132 @@
+"""GPU parity tests of the complex Arnoldi path (znaupd_c/zneupd_c, cnaupd_c/cneupd_c): the CUDA
+path through the C-ABI against the CPU oracle (oracle/ref_impl_complex.inc) on the same seeded inputs.  Tolerances as for
+the real path: eigenvalues 1e-10 relative (complex128) / 1e-4 (complex64), ||A x - lambda x|| small, identical nconv,
+restart count and OP*x count."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from backends import Oracle
+from problems import complex_convdiff2d, complex_tridiag
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import arpack_ng_b200 as m
+    m.lib()
+    return m
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev_op(A):
+    """y = A x for a scipy CSR complex matrix, on the device (torch sparse CSR; the OP belongs to the caller)."""
+    torch = _torch()
+    At = torch.sparse_csr_tensor(torch.as_tensor(A.indptr.astype(np.int64)), torch.as_tensor(A.indices.astype(np.int64)),
+                                 torch.as_tensor(A.data), size=A.shape, dtype=torch.as_tensor(A.data).dtype).cuda()
+
+    def op(x, y, *_):
+        y.copy_(torch.mv(At, x))
+    return op
+
+
+def _start(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+
+
+def _counts(r):
+    return int(r.nconv), int(r.iparam[2]), int(r.iparam[8]), int(r.iparam[10])
+
+
+@pytest.mark.parametrize("name,which", [("tridiag", "LM"), ("tridiag", "SR"), ("tridiag", "SM"), ("conv2d", "LR"),
+                                        ("rot_conv2d", "LI"), ("rot_conv2d", "SI")])
+def test_znaupd_device_vs_oracle(ab, name, which):
+    # rot_conv2d = i * conv2d: the well-separated real ends of the spectrum become its imaginary ends (LI / SI)
+    A = {"tridiag": lambda: complex_tridiag(300), "conv2d": lambda: complex_convdiff2d(24),
+         "rot_conv2d": lambda: (1j * complex_convdiff2d(24)).tocsr()}[name]()
+    n, nev, ncv = A.shape[0], 4, 20
+    r0 = _start(n, 5)
+    r = ab.solve_complex(_dev_op(A), n, nev, ncv, which, tol=1e-10, mxiter=3000, resid=r0)
+    ref = Oracle().solve_complex(lambda x: A @ x, n, nev, ncv, which, tol=1e-10, mxiter=3000, resid=r0, c_abi_tol=True)
+    assert r.info == ref.info == 0 and r.ierr == ref.ierr == 0
+    assert _counts(r) == _counts(ref)
+    assert np.abs(r.d - ref.d).max() <= 1e-10 * np.abs(ref.d).max()
+    Z = r.z.cpu().numpy().reshape(ncv, n)[:nev].T
+    res = np.linalg.norm(A @ Z - Z * r.d[None, :], axis=0)
+    assert (res <= 1e-8 * np.abs(r.d).max()).all(), res
+    assert np.abs(np.linalg.norm(Z, axis=0) - 1).max() < 1e-10
+    assert ab.launch_stats()["kernels"] > 0
+
+
+def test_znaupd_host_buffers_match_device_buffers(ab):
+    """An unmodified CPU caller (host resid/v/workd, CPU OP) and the device-pointer caller run the same kernels."""
+    A = complex_tridiag(257)
+    n, nev, ncv = A.shape[0], 3, 16
+    r0 = _start(n, 9)
+
+    def op_host(x, y, *_):
+        y[:] = A @ x
+    rd = ab.solve_complex(_dev_op(A), n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0)
+    rh = ab.solve_complex(op_host, n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0, host_buffers=True)
+    assert rd.info == rh.info == 0 and rd.ierr == rh.ierr == 0
+    assert _counts(rd)[:3] == _counts(rh)[:3]
+    assert np.abs(rd.d - rh.d).max() <= 1e-10 * np.abs(rd.d).max()
+    Z = rh.z.reshape(ncv, n)[:nev].T
+    assert (np.linalg.norm(A @ Z - Z * rh.d[None, :], axis=0) <= 1e-8 * np.abs(rh.d).max()).all()
+
+
+def test_cnaupd_single_precision(ab):
+    A = complex_tridiag(200, imag_span=20.0).astype(np.complex64)
+    n, nev, ncv = A.shape[0], 3, 16
+    r0 = _start(n, 2).astype(np.complex64)
+    r = ab.solve_complex(_dev_op(A), n, nev, ncv, "LM", tol=1e-5, mxiter=3000, resid=r0, dtype=np.complex64)
+    ref = Oracle().solve_complex(lambda x: A @ x, n, nev, ncv, "LM", tol=1e-5, mxiter=3000, resid=r0,
+                                 dtype=np.complex64, c_abi_tol=True)
+    assert r.info == ref.info == 0 and r.ierr == 0
+    assert r.nconv == ref.nconv == nev
+    assert np.abs(np.sort_complex(r.d) - np.sort_complex(ref.d)).max() <= 1e-4 * np.abs(ref.d).max()
+
+
+def test_znaupd_shift_invert_mode3(ab):
+    """Mode 3 (zndrv2-style): OP = inv(A - sigma I), eigenvalues of A nearest sigma; exercises the back-transform and
+    the zgeru purification of zneupd (zneupd.f:820-868).  The caller's OP is a CPU sparse LU, so host buffers."""
+    A = complex_tridiag(220)
+    n, nev, ncv = A.shape[0], 4, 20
+    sigma = 50000.0 + 20.0j
+    lu = spla.splu((A - sigma * __import__("scipy.sparse").sparse.eye(n)).tocsc())
+    r0 = _start(n, 4)
+
+    def op_host(x, y, *_):
+        y[:] = lu.solve(np.ascontiguousarray(x))
+    r = ab.solve_complex(op_host, n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0, mode=3, sigma=sigma,
+                         host_buffers=True)
+    ref = Oracle().solve_complex(lambda x: lu.solve(np.ascontiguousarray(x)), n, nev, ncv, "LM", tol=1e-10, mxiter=3000,
+                                 resid=r0, mode=3, sigma=sigma, c_abi_tol=True)
+    assert r.info == ref.info == 0 and r.ierr == ref.ierr == 0
+    assert _counts(r)[:3] == _counts(ref)[:3]
+    assert np.abs(r.d - ref.d).max() <= 1e-10 * np.abs(ref.d).max()
+    Z = r.z.reshape(ncv, n)[:nev].T
+    assert (np.linalg.norm(A @ Z - Z * r.d[None, :], axis=0) <= 1e-7 * np.abs(r.d).max()).all()
+    dense = np.linalg.eigvals(A.toarray())
+    want = dense[np.argsort(np.abs(dense - sigma))[:nev]]
+    assert np.abs(np.sort_complex(r.d) - np.sort_complex(want)).max() <= 1e-8 * np.abs(want).max()
+
+
+def test_znaupd_argument_errors_and_no_vectors(ab):
+    A = complex_tridiag(64)
+    n = A.shape[0]
+    r = ab.solve_complex(_dev_op(A), n, 3, 3, "LM", eupd=False)          # ncv <= nev
+    assert r.info == -3
+    r = ab.solve_complex(_dev_op(A), n, 3, 12, "LA", eupd=False)         # which of the symmetric family
+    assert r.info == -5
+    r0 = _start(n, 1)
+    a = ab.solve_complex(_dev_op(A), n, 3, 12, "LM", tol=1e-10, mxiter=3000, resid=r0)
+    b = ab.solve_complex(_dev_op(A), n, 3, 12, "LM", tol=1e-10, mxiter=3000, resid=r0, rvec=False)
+    assert a.info == b.info == 0 and b.ierr == 0
+    assert np.abs(np.sort_complex(a.d) - np.sort_complex(b.d)).max() <= 1e-10 * np.abs(a.d).max()
