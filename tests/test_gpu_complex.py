@@ -130,3 +130,34 @@ def test_znaupd_argument_errors_and_no_vectors(ab):
     b = ab.solve_complex(_dev_op(A), n, 3, 12, "LM", tol=1e-10, mxiter=3000, resid=r0, rvec=False)
     assert a.info == b.info == 0 and b.ierr == 0
     assert np.abs(np.sort_complex(a.d) - np.sort_complex(b.d)).max() <= 1e-10 * np.abs(a.d).max()
+
+
+def test_icb_arpack_c_zn(ab):
+    """TESTS/icb_arpack_c.c:98-165 through the C-ABI on the device: A = diag((i+1)(1+i)), nev=9, ncv=19, 'LM',
+    tol=1e-6, rvec=0, random start (zlarnv stream) -> d[i] = (992+i)(1+i), 1e-5 per component."""
+    torch = _torch()
+    n, nev, ncv = 1000, 9, 19
+    diag = torch.arange(1, n + 1, dtype=torch.float64, device="cuda") * (1 + 1j)
+    ab.lib().ab200_reset_seed()
+    r = ab.solve_complex(lambda x, y, *_: torch.mul(diag, x, out=y), n, nev, ncv, "LM", tol=1e-6, mxiter=10 * n,
+                         rvec=False)
+    assert r.info == 0 and r.ierr == 0 and r.nconv >= nev
+    want = (n - (nev - 1) + np.arange(nev)) * (1 + 1j)
+    assert np.abs(r.d.real - want.real).max() <= 1e-5 and np.abs(r.d.imag - want.imag).max() <= 1e-5
+    ref = Oracle().solve_complex(lambda x: np.arange(1, n + 1) * (1 + 1j) * x, n, nev, ncv, "LM", tol=1e-6,
+                                 mxiter=10 * n, rvec=False, c_abi_tol=True)
+    assert _counts(r)[:3] == _counts(ref)[:3]     # same zlarnv start vector, same path
+
+
+import golden_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("c", golden_cases.load_complex(), ids=golden_cases.case_id)
+def test_cuda_path_reproduces_committed_scipy_znaupd_vectors(ab, c):
+    """Golden vectors made by an implementation that is not ours (SciPy's C translation of znaupd/zneupd): identical
+    nconv, restart and OP*x counts, eigenvalues to 1e-10, through the C-ABI on the device."""
+    A = golden_cases.ZPROBLEMS[c["problem"]]()
+    n = A.shape[0]
+    r = ab.solve_complex(_dev_op(A), n, c["nev"], c["ncv"], c["which"], tol=c["tol"], mxiter=3000,
+                         resid=golden_cases.start_vector_complex(c, n))
+    golden_cases.check_against_golden_complex(c, r)
