@@ -142,6 +142,62 @@ static int nonsym_bind_c(void) {
   return 0;
 }
 
+/* 5. znaupd_c / zneupd_c from C99 (a_dcomplex = double _Complex here, a struct on the library's C++ side):
+ *    (a) TESTS/icb_arpack_c.c:98-165 -- A = diag((i+1)(1+i)), nev=9, ncv=19, 'LM', tol=1e-6, rvec=0;
+ *    (b) shift-invert, mode 3, on the same diagonal matrix: sigma is passed BY VALUE as a C complex and must arrive
+ *        intact, otherwise the back-transformed eigenvalues 1/theta + sigma are wrong. */
+static int complex_bind_c(void) {
+  enum { N = 1000, NEV = 9, NCV = 19, LWORKL = NCV * (3 * NCV + 5) };
+  static a_dcomplex resid[N], v[N * NCV], workd[3 * N], workl[LWORKL], d[NEV + 1], z[N * NEV], workev[2 * NCV];
+  static double rwork[NCV];
+  a_int iparam[11] = {0}, ipntr[14] = {0}, select[NCV];
+  a_int ido = 0, info = 0;
+  iparam[0] = 1; iparam[2] = 10 * N; iparam[3] = 1; iparam[6] = 1;
+  do {
+    znaupd_c(&ido, "I", N, "LM", NEV, 1e-6, resid, NCV, v, N, iparam, ipntr, workd, workl, LWORKL, rwork, &info);
+    if (ido == 1 || ido == -1) {
+      const a_dcomplex* x = workd + ipntr[0] - 1;
+      a_dcomplex* y = workd + ipntr[1] - 1;
+      for (int i = 0; i < N; ++i) y[i] = x[i] * CMPLX(i + 1.0, i + 1.0);
+    }
+  } while (ido == 1 || ido == -1);
+  if (info == -9990) return 3;
+  if (info < 0 || iparam[4] < NEV) return fail("znaupd_c info/nconv", info, iparam[4]);
+  zneupd_c(0, "A", select, d, z, N, CMPLX(0.0, 0.0), workev, "I", N, "LM", NEV, 1e-6, resid, NCV, v, N, iparam, ipntr,
+           workd, workl, LWORKL, rwork, &info);
+  if (info < 0) return fail("zneupd_c info", info, 0);
+  for (int i = 0; i < NEV; ++i) {
+    const double ref = N - (NEV - 1) + i;
+    if (fabs(creal(d[i]) - ref) > 1e-5 || fabs(cimag(d[i]) - ref) > 1e-5) return fail("znaupd_c eigenvalue", creal(d[i]), ref);
+  }
+  /* (b) mode 3 around sigma = 500.3 + 500.2i: the nearest eigenvalues are (500+k)(1+i) */
+  const a_dcomplex sigma = CMPLX(500.3, 500.2);
+  ido = 0; info = 0;
+  iparam[0] = 1; iparam[2] = 10 * N; iparam[3] = 1; iparam[6] = 3;
+  do {
+    znaupd_c(&ido, "I", N, "LM", 4, 1e-10, resid, NCV, v, N, iparam, ipntr, workd, workl, LWORKL, rwork, &info);
+    if (ido == 1 || ido == -1) {
+      const a_dcomplex* x = workd + ipntr[0] - 1;
+      a_dcomplex* y = workd + ipntr[1] - 1;
+      for (int i = 0; i < N; ++i) y[i] = x[i] / (CMPLX(i + 1.0, i + 1.0) - sigma);
+    }
+  } while (ido == 1 || ido == -1);
+  if (info != 0 || iparam[4] < 4) return fail("znaupd_c mode 3 info/nconv", info, iparam[4]);
+  zneupd_c(1, "A", select, d, z, N, sigma, workev, "I", N, "LM", 4, 1e-10, resid, NCV, v, N, iparam, ipntr, workd, workl,
+           LWORKL, rwork, &info);
+  if (info != 0) return fail("zneupd_c mode 3 info", info, 0);
+  for (int k = 0; k < 4; ++k) {
+    /* every returned value must be a diagonal entry m(1+i) with m in 499..502 */
+    const double m = floor(creal(d[k]) + 0.5);
+    if (m < 499 || m > 502 || fabs(creal(d[k]) - m) > 1e-7 || fabs(cimag(d[k]) - m) > 1e-7)
+      return fail("zneupd_c mode 3 eigenvalue (sigma by value)", creal(d[k]), cimag(d[k]));
+    /* and z(:,k) the matching unit vector up to a phase */
+    if (fabs(cabs(z[(size_t)k * N + (int)m - 1]) - 1.0) > 1e-7) return fail("zneupd_c mode 3 eigenvector", cabs(z[(size_t)k * N + (int)m - 1]), 1.0);
+  }
+  printf("icb_caller: znaupd_c/zneupd_c OK\n");
+  return 0;
+}
+
 /* 4. argument errors come back as info < 0 with ido = 99, never as an abort (dsaupd.f:539-543) */
 static int argument_errors(void) {
   enum { N = 50, NCV = 10, LWORKL = NCV * NCV + 8 * NCV };
@@ -162,7 +218,7 @@ static int argument_errors(void) {
 int main(void) {
   debug_c(6, -3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
   sstats_c();
-  int (*parts[])(void) = {sym_bind_c, sym_fortran_abi, nonsym_bind_c, argument_errors};
+  int (*parts[])(void) = {sym_bind_c, sym_fortran_abi, nonsym_bind_c, argument_errors, complex_bind_c};
   for (unsigned k = 0; k < sizeof(parts) / sizeof(parts[0]); ++k) {
     const int rc = parts[k]();
     if (rc == 3) {

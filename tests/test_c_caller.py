@@ -44,5 +44,5 @@ def test_c_caller_reproduces_reference_answers_on_gpu():
     p = subprocess.run([_EXE], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     for part in ("dsaupd_c/dseupd_c OK", "dsaupd_/dseupd_ (Fortran ABI) OK", "dnaupd_c/dneupd_c OK",
-                 "argument errors OK", "all checks passed"):
+                 "argument errors OK", "znaupd_c/zneupd_c OK", "all checks passed"):
         assert part in p.stdout

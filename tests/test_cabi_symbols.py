@@ -31,7 +31,8 @@ def test_header_declares_the_reference_entry_points():
     names = declared_functions()
     for must in ["dsaupd_c", "dseupd_c", "dnaupd_c", "dneupd_c", "ssaupd_c", "sseupd_c", "snaupd_c", "sneupd_c",
                  "pdsaupd_c", "pdseupd_c", "pdnaupd_c", "pdneupd_c", "pssaupd_c", "psseupd_c", "psnaupd_c", "psneupd_c",
-                 "dsaupd_", "dseupd_", "dnaupd_", "dneupd_", "debug_c", "stat_c", "sstats_c", "sstatn_c"]:
+                 "dsaupd_", "dseupd_", "dnaupd_", "dneupd_", "debug_c", "stat_c", "sstats_c", "sstatn_c",
+                 "znaupd_c", "zneupd_c", "cnaupd_c", "cneupd_c", "znaupd_", "zneupd_"]:
         assert must in names, must
     assert len(names) >= 45
 
