@@ -157,15 +157,19 @@ __global__ void __launch_bounds__(kThreads) k_zupdate(int64_t n, int j, const ty
   R nrm = R(0);
   for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
     const C* vr = v + r;
-    C a0 = mk<C>(R(0), R(0)), a1 = a0;
+    C a0 = mk<C>(R(0), R(0)), a1 = a0, a2 = a0, a3 = a0;
     int k = 0;
-    for (; k + 2 <= j; k += 2) {
-      fma_cplx(a0, vr[(int64_t)(k + 0) * ldv], cs[k + 0]);
-      fma_cplx(a1, vr[(int64_t)(k + 1) * ldv], cs[k + 1]);
+    for (; k + 4 <= j; k += 4) {
+      const C v0 = vr[(int64_t)(k + 0) * ldv], v1 = vr[(int64_t)(k + 1) * ldv];
+      const C v2 = vr[(int64_t)(k + 2) * ldv], v3 = vr[(int64_t)(k + 3) * ldv];
+      fma_cplx(a0, v0, cs[k + 0]);
+      fma_cplx(a1, v1, cs[k + 1]);
+      fma_cplx(a2, v2, cs[k + 2]);
+      fma_cplx(a3, v3, cs[k + 3]);
     }
     for (; k < j; ++k) fma_cplx(a0, vr[(int64_t)k * ldv], cs[k]);
     const C s = src[r];
-    const C d = mk<C>(s.x - (a0.x + a1.x), s.y - (a0.y + a1.y));
+    const C d = mk<C>(s.x - ((a0.x + a1.x) + (a2.x + a3.x)), s.y - ((a0.y + a1.y) + (a2.y + a3.y)));
     dst[r] = d;
     nrm += d.x * d.x + d.y * d.y;
   }
@@ -306,18 +310,29 @@ __global__ void __launch_bounds__(kThreads) k_zvq(int64_t n, int kin, int kout, 
     __syncthreads();
     for (int r = threadIdx.x; r < nr; r += kThreads) {
       C bval = mk<C>(R(0), R(0));
-      for (int c = 0; c < kout; ++c) {
-        const C* qc = q + (size_t)c * kin;
-        C a0 = mk<C>(R(0), R(0)), a1 = a0;
-        int k = 0;
-        for (; k + 2 <= kin; k += 2) {
-          fma_cplx(a0, tile[(k + 0) * rows + r], __ldg(qc + k + 0));
-          fma_cplx(a1, tile[(k + 1) * rows + r], __ldg(qc + k + 1));
+      // four output columns per pass over the staged row: one shared-memory read feeds four complex FMAs
+      for (int c0 = 0; c0 < kout; c0 += 4) {
+        const int nc = (kout - c0 < 4) ? (kout - c0) : 4;
+        const C* q0 = q + (size_t)c0 * kin;
+        const C* q1 = q0 + (nc > 1 ? kin : 0);
+        const C* q2 = q0 + (nc > 2 ? 2 * kin : 0);
+        const C* q3 = q0 + (nc > 3 ? 3 * kin : 0);
+        C a0 = mk<C>(R(0), R(0)), a1 = a0, a2 = a0, a3 = a0;
+        for (int k = 0; k < kin; ++k) {
+          const C t = tile[k * rows + r];
+          fma_cplx(a0, t, __ldg(q0 + k));
+          fma_cplx(a1, t, __ldg(q1 + k));
+          fma_cplx(a2, t, __ldg(q2 + k));
+          fma_cplx(a3, t, __ldg(q3 + k));
         }
-        for (; k < kin; ++k) fma_cplx(a0, tile[k * rows + r], __ldg(qc + k));
-        const C a = mk<C>(a0.x + a1.x, a0.y + a1.y);
-        out[r0 + r + (int64_t)c * ldo] = a;
-        if (c == beta_col) bval = a;
+        const C acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc < nc) {
+            out[r0 + r + (int64_t)(c0 + cc) * ldo] = acc[cc];
+            if (c0 + cc == beta_col) bval = acc[cc];
+          }
+        }
       }
       if (with_resid) {
         C tr = mk<C>(R(0), R(0));
@@ -430,7 +445,7 @@ void CudaVecOpsZ<R>::ger(int64_t n, int k, const T* resid, const T* w_host, T* z
 template <typename R>
 void CudaVecOpsZ<R>::dots(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* out) {
   using C = typename Vec2<R>::type;
-  constexpr int CC = 4;
+  constexpr int CC = 8;  // columns per register chunk: x is re-read once per chunk (12.5 % of the V traffic, from L2)
   const int grid = reduce_grid(n);
   const int pcols = j + 1;
   C* part = reinterpret_cast<C*>(partial((size_t)grid * pcols));
