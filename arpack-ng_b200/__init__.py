@@ -106,6 +106,9 @@ def lib():
     L.ab200_debug_orth_f64.argtypes = [C.c_longlong, C.c_int, vp, C.c_longlong, vp, vp, vp]
     L.ab200_debug_vq_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp, C.c_double, C.c_double,
                                      C.c_int, vp, vp]
+    L.ab200_debug_zorth_f64.argtypes = [C.c_longlong, C.c_int, vp, C.c_longlong, vp, vp, vp]
+    L.ab200_debug_zvq_f64.argtypes = [C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong, vp, vp, C.c_longlong, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_int, vp, C.POINTER(C.c_double)]
     L.ab200_profile_enable.argtypes = [C.c_int]
     L.ab200_profile_get.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
                                     C.POINTER(C.c_double)]

@@ -274,6 +274,49 @@ void ab200_cneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* 
                      info);
 }
 
+// Kernel unit-test hooks (tests/test_gpu_complex.py): ONE orthogonalisation pass / ONE restart update of the complex
+// path on caller-supplied DEVICE arrays (interleaved complex128), results handed back to host arrays, so that each
+// kernel can be compared with a plain numpy statement of the same op independently of the solver.
+//   out_host (complex, j + 2 entries) = { h = V_j^H w (j), sum conj(w) w, sum |r|^2 } with r = w - V_j h written to resid
+int ab200_debug_zorth_f64(long long n, int j, const void* v, long long ldv, const void* w, void* resid, void* out_host) {
+  try {
+    require_device_z();
+    CudaVecOpsZ<double> ops((cudaStream_t)ab200_get_stream());
+    zd* mb = ops.mailbox((size_t)j + 4);
+    ops.dots(n, j, (const zd*)v, ldv, (const zd*)w, (const zd*)w, mb);
+    ops.update(n, j, (const zd*)v, ldv, mb, (const zd*)w, (zd*)resid, mb + j + 1);
+    ops.fetch((zd*)out_host, mb, (size_t)j + 2);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: debug_zorth: %s\n", e.what());
+    return -1;
+  }
+}
+// out(:,0:kout) = V(:,0:kin)*Q (q_host column-major kin x kout, interleaved complex128); out == v is allowed (in place);
+// resid <- sigma*resid + beta*out(:,beta_col) (beta_col < 0: no beta term); nrm2_host[0] = sum |resid|^2
+int ab200_debug_zvq_f64(long long n, int kin, int kout, const void* v, long long ldv, const void* q_host, void* out,
+                        long long ldo, double sigma_re, double sigma_im, double beta_re, double beta_im, int beta_col,
+                        void* resid, double* nrm2_host) {
+  try {
+    require_device_z();
+    CudaVecOpsZ<double> ops((cudaStream_t)ab200_get_stream());
+    zd* mb = ops.mailbox(4);
+    if (out == v) {
+      ops.vq_update(n, kin, kout, (zd*)out, ldv, (const zd*)q_host, kin, resid != nullptr, zd(sigma_re, sigma_im),
+                    zd(beta_re, beta_im), beta_col, (zd*)resid, mb);
+    } else {
+      ops.vq_out(n, kin, kout, (const zd*)v, ldv, (const zd*)q_host, kin, (zd*)out, ldo);
+    }
+    zd h(0);
+    ops.fetch(&h, mb, 1);
+    nrm2_host[0] = h.real();
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "arpack_b200: debug_zvq: %s\n", e.what());
+    return -1;
+  }
+}
+
 // legacy Fortran ABI (gfortran: everything by reference, CHARACTER lengths appended)
 void znaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, a_dcomplex* resid,
              a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,

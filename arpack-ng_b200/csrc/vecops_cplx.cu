@@ -279,10 +279,13 @@ __global__ void k_zger(int64_t n, int k, const typename Vec2<R>::type* __restric
   }
 }
 
-// out(:,0:kout) = V(:,0:kin) * Q (kin x kout, column-major, packed) for a tile of `rows` rows per CTA iteration.  The
-// whole tile of V is staged in shared memory (tile[k][r], conflict-free: a warp reads 32 consecutive rows of one
-// column) before anything is written, so out may alias V.  Optional fused
-// resid = sigma*resid + beta*out(:,beta_col) and its squared norm.
+// out(:,0:kout) = V(:,0:kin) * Q (kin x kout, column-major, packed), `rows` (32 or 64) rows per tile.  The whole
+// tile of V is staged in shared memory (tile[k][r]: a warp reads 32 consecutive rows of one column, conflict-free)
+// before anything is written, so out may alias V.  The 256 threads of a CTA form 256/rows column groups; a thread
+// owns one row and computes two output columns per pass (one shared-memory read feeds two complex FMAs).  The tile is
+// small (kin KB at 64 rows), so several CTAs are resident per SM and one CTA's loads overlap another's arithmetic.
+// Optional fused resid = sigma*resid + beta*out(:,beta_col) and its squared norm (done by the thread that owns
+// column beta_col of the row; by column group 0 when there is no beta term).
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_zvq(int64_t n, int kin, int kout, int rows,
                                                   const typename Vec2<R>::type* v, int64_t ldv,
@@ -298,48 +301,41 @@ __global__ void __launch_bounds__(kThreads) k_zvq(int64_t n, int kin, int kout, 
   C* tile = reinterpret_cast<C*>(smem_raw);
   __shared__ R red[kWarps];
   R nrm = R(0);
+  const int ngroups = kThreads / rows;        // 4 (rows = 64) or 8 (rows = 32)
+  const int r = threadIdx.x % rows;           // my row inside the tile
+  const int g = threadIdx.x / rows;           // my column group
+  const int owner_col = (beta_col >= 0) ? beta_col : 0;
   const int64_t ntiles = (n + rows - 1) / rows;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t r0 = t * rows;
     const int nr = (int)((n - r0 < rows) ? (n - r0) : rows);
     __syncthreads();  // the previous tile has been consumed
     for (int idx = threadIdx.x; idx < kin * rows; idx += kThreads) {
-      const int k = idx / rows, r = idx - k * rows;
-      if (r < nr) tile[idx] = v[r0 + r + (int64_t)k * ldv];
+      const int k = idx / rows, rr = idx - k * rows;
+      if (rr < nr) tile[idx] = v[r0 + rr + (int64_t)k * ldv];
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < nr; r += kThreads) {
-      C bval = mk<C>(R(0), R(0));
-      // four output columns per pass over the staged row: one shared-memory read feeds four complex FMAs
-      for (int c0 = 0; c0 < kout; c0 += 4) {
-        const int nc = (kout - c0 < 4) ? (kout - c0) : 4;
+    if (r < nr) {
+      for (int c0 = 2 * g; c0 < kout; c0 += 2 * ngroups) {
+        const bool two = (c0 + 1 < kout);
         const C* q0 = q + (size_t)c0 * kin;
-        const C* q1 = q0 + (nc > 1 ? kin : 0);
-        const C* q2 = q0 + (nc > 2 ? 2 * kin : 0);
-        const C* q3 = q0 + (nc > 3 ? 3 * kin : 0);
-        C a0 = mk<C>(R(0), R(0)), a1 = a0, a2 = a0, a3 = a0;
+        const C* q1 = q0 + (two ? kin : 0);
+        C a0 = mk<C>(R(0), R(0)), a1 = a0;
         for (int k = 0; k < kin; ++k) {
-          const C t = tile[k * rows + r];
-          fma_cplx(a0, t, __ldg(q0 + k));
-          fma_cplx(a1, t, __ldg(q1 + k));
-          fma_cplx(a2, t, __ldg(q2 + k));
-          fma_cplx(a3, t, __ldg(q3 + k));
+          const C tv = tile[k * rows + r];
+          fma_cplx(a0, tv, __ldg(q0 + k));
+          fma_cplx(a1, tv, __ldg(q1 + k));
         }
-        const C acc[4] = {a0, a1, a2, a3};
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cc < nc) {
-            out[r0 + r + (int64_t)(c0 + cc) * ldo] = acc[cc];
-            if (c0 + cc == beta_col) bval = acc[cc];
-          }
+        out[r0 + r + (int64_t)c0 * ldo] = a0;
+        if (two) out[r0 + r + (int64_t)(c0 + 1) * ldo] = a1;
+        if (with_resid && (c0 == owner_col || (two && c0 + 1 == owner_col))) {
+          const C bval = (c0 == owner_col) ? a0 : a1;
+          C tr = mk<C>(R(0), R(0));
+          fma_cplx(tr, sigma, resid[r0 + r]);
+          if (beta_col >= 0) fma_cplx(tr, beta, bval);
+          resid[r0 + r] = tr;
+          nrm += tr.x * tr.x + tr.y * tr.y;
         }
-      }
-      if (with_resid) {
-        C tr = mk<C>(R(0), R(0));
-        fma_cplx(tr, sigma, resid[r0 + r]);
-        if (beta_col >= 0) fma_cplx(tr, beta, bval);
-        resid[r0 + r] = tr;
-        nrm += tr.x * tr.x + tr.y * tr.y;
       }
     }
   }
@@ -350,10 +346,10 @@ __global__ void __launch_bounds__(kThreads) k_zvq(int64_t n, int kin, int kout, 
   if (lane == 0) red[warp] = nrm;
   __syncthreads();
   if (threadIdx.x == 0) {
-    R s = R(0);
+    R s2 = R(0);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += red[w];
-    partial[blockIdx.x] = mk<C>(s, R(0));
+    for (int w = 0; w < kWarps; ++w) s2 += red[w];
+    partial[blockIdx.x] = mk<C>(s2, R(0));
   }
   finish_grid_reduce2(partial, 1, 1, nrm2_out, ticket);
 }
@@ -476,20 +472,22 @@ void CudaVecOpsZ<R>::vq(int64_t n, int kin, int kout, const T* v, int64_t ldv, c
     if (with_resid) axpby_norm(n, sigma, T(0), nullptr, resid, nrm2);
     return;
   }
-  // rows per tile: as many as fit next to nothing else in ~200 KB, a multiple of 32, at most 256
+  // 64 rows per tile (32 beyond 200 columns): the tile takes kin KB of shared memory, so up to 8 CTAs share an SM
   const size_t budget = 200 * 1024;
-  int rows = (int)(budget / (sizeof(T) * (size_t)kin)) / 32 * 32;
-  if (rows > kThreads) rows = kThreads;
-  if (rows < 32) throw CudaError("complex V*Q: ncv too large for the shared-memory tile (ncv <= 400 supported)");
+  int rows = 64;
+  if (sizeof(T) * (size_t)kin * rows > budget) rows = 32;
   const size_t smem = sizeof(T) * (size_t)kin * rows;
+  if (smem > budget) throw CudaError("complex V*Q: ncv too large for the shared-memory tile (ncv <= 400 supported)");
   static size_t attr_set[2] = {0, 0};
   size_t& cur = attr_set[sizeof(R) == 8 ? 0 : 1];
-  if (smem > cur) {
+  if (smem > 48 * 1024 && cur < budget) {
     AB200_CUDA_CHECK(cudaFuncSetAttribute(k_zvq<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     cur = budget;
   }
   const int64_t ntiles = (n + rows - 1) / rows;
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms_);
+  int per_sm = (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms_ * per_sm);
   C* part = reinterpret_cast<C*>(partial((size_t)grid));
   ProfScope ps(stream_, "zvq", (double)sizeof(T) * n * (kin + kout + (with_resid ? 2.0 : 0.0)));
   k_zvq<R><<<grid, kThreads, smem, stream_>>>(n, kin, kout, rows, reinterpret_cast<const C*>(v), ldv,

@@ -212,6 +212,11 @@ int ab200_debug_vq_f64(long long n, int kin, int kout, double* v, long long ldv,
                        double beta, int beta_col, double* resid, double* nrm2_host);
 /* kernel micro-benchmark on synthetic data (tools/kernel_sweep.py): what = 0 orth step, 1 multi-dots, 2 V*Q update */
 int ab200_kernel_probe_f64(long long n, int j, int ncv, int iters, int what, int kout);
+/* the same hooks for the complex kernels (device arrays of interleaved complex128; see api_cplx.cu) */
+int ab200_debug_zorth_f64(long long n, int j, const void* v, long long ldv, const void* w, void* resid, void* out_host);
+int ab200_debug_zvq_f64(long long n, int kin, int kout, const void* v, long long ldv, const void* q_host, void* out,
+                        long long ldo, double sigma_re, double sigma_im, double beta_re, double beta_im, int beta_col,
+                        void* resid, double* nrm2_host);
 int ab200_device_count(void);
 const char* ab200_version(void);
 

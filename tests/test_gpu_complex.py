@@ -161,3 +161,74 @@ def test_cuda_path_reproduces_committed_scipy_znaupd_vectors(ab, c):
     r = ab.solve_complex(_dev_op(A), n, c["nev"], c["ncv"], c["which"], tol=c["tol"], mxiter=3000,
                          resid=golden_cases.start_vector_complex(c, n))
     golden_cases.check_against_golden_complex(c, r)
+
+
+# --------------------------------------------------------------------------------------------------
+# per-kernel tests: each complex kernel against a plain numpy statement of the same op
+# --------------------------------------------------------------------------------------------------
+def _crand(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+@pytest.mark.parametrize("n,j,pad", [(1, 1, 0), (37, 5, 0), (1000, 8, 3), (1000, 9, 0), (100003, 31, 1),
+                                     (65536, 64, 0), (4099, 70, 5)])
+def test_kernel_zdots_zupdate_vs_numpy(ab, n, j, pad):
+    """k_zdots (h = V_j^H w, sum conj(w) w) and k_zupdate (r = w - V_j h, sum |r|^2) on odd sizes, column counts around
+    the 8-column register chunk, padded leading dimensions."""
+    torch = _torch()
+    rng = np.random.default_rng(n + j)
+    ldv = n + pad
+    V = np.zeros((j, ldv), dtype=complex)       # column-major (ldv, j)
+    V[:, :n] = _crand(rng, j, n) / np.sqrt(n)
+    w = _crand(rng, n)
+    Vd, wd = torch.as_tensor(V.ravel()).cuda(), torch.as_tensor(w).cuda()
+    rd = torch.zeros(n, dtype=torch.complex128, device="cuda")
+    out = np.zeros(j + 2, dtype=complex)
+    assert ab.lib().ab200_debug_zorth_f64(n, j, Vd.data_ptr(), ldv, wd.data_ptr(), rd.data_ptr(), out.ctypes.data) == 0
+    Vn = V[:, :n].T                              # n x j
+    h = Vn.conj().T @ w
+    r = w - Vn @ h
+    scale = np.abs(h).max() + 1e-300
+    assert np.abs(out[:j] - h).max() <= 1e-12 * max(scale, 1.0)
+    assert abs(out[j] - np.vdot(w, w)) <= 1e-12 * abs(np.vdot(w, w)) and abs(out[j].imag) <= 1e-12 * abs(out[j].real)
+    # the device used ITS h for the update: compare against numpy's r up to that difference
+    assert np.abs(rd.cpu().numpy() - r).max() <= 1e-11 * max(1.0, np.abs(w).max())
+    assert abs(out[j + 1].real - np.vdot(r, r).real) <= 1e-10 * np.vdot(r, r).real and out[j + 1].imag == 0.0
+
+
+@pytest.mark.parametrize("n,kin,kout,beta_col,inplace", [(1, 3, 2, 1, True), (1000, 20, 7, 6, True), (1001, 20, 8, -1, True),
+                                                         (70000, 30, 30, -1, True), (4097, 64, 21, 20, True),
+                                                         (513, 12, 5, -1, False), (3000, 210, 9, 8, True)])
+def test_kernel_zvq_vs_numpy(ab, n, kin, kout, beta_col, inplace):
+    """k_zvq: V(:,0:kout) <- V(:,0:kin) Q in place (or into a separate array), resid <- sigma resid + beta Vnew(:,col)
+    and its squared norm; tile sizes 64 and 32 rows (kin > 200), column counts that are not multiples of the groups."""
+    torch = _torch()
+    rng = np.random.default_rng(n + kin + kout)
+    ldv = n + 2
+    V = np.zeros((kin, ldv), dtype=complex)
+    V[:, :n] = _crand(rng, kin, n)
+    Q = _crand(rng, kout, kin)                   # column-major kin x kout
+    resid = _crand(rng, n)
+    sigma, beta = complex(0.3, -0.7), complex(-1.1, 0.4)
+    Vd = torch.as_tensor(V.ravel()).cuda()
+    rd = torch.as_tensor(resid).cuda()
+    nrm = np.zeros(1)
+    want = V[:, :n].T @ Q.T                      # n x kout
+    L = ab.lib()
+    if inplace:
+        assert L.ab200_debug_zvq_f64(n, kin, kout, Vd.data_ptr(), ldv, Q.ctypes.data, Vd.data_ptr(), ldv, sigma.real,
+                                     sigma.imag, beta.real, beta.imag, beta_col, rd.data_ptr(),
+                                     nrm.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))) == 0
+        got = Vd.cpu().numpy().reshape(kin, ldv)[:kout, :n].T
+        rwant = sigma * resid + (beta * want[:, beta_col] if beta_col >= 0 else 0.0)
+        assert np.abs(rd.cpu().numpy() - rwant).max() <= 1e-11 * max(1.0, np.abs(rwant).max())
+        assert abs(nrm[0] - np.vdot(rwant, rwant).real) <= 1e-10 * np.vdot(rwant, rwant).real
+        # columns kout..kin of V are untouched
+        assert np.array_equal(Vd.cpu().numpy().reshape(kin, ldv)[kout:, :n], V[kout:, :n])
+    else:
+        Od = torch.zeros(kout * n, dtype=torch.complex128, device="cuda")
+        assert L.ab200_debug_zvq_f64(n, kin, kout, Vd.data_ptr(), ldv, Q.ctypes.data, Od.data_ptr(), n, 0.0, 0.0, 0.0, 0.0,
+                                     -1, None, nrm.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))) == 0
+        got = Od.cpu().numpy().reshape(kout, n).T
+        assert np.array_equal(Vd.cpu().numpy(), V.ravel())
+    assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
