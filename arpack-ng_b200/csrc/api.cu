@@ -513,6 +513,9 @@ void debug_c(a_int logfil, a_int ndigit, a_int mgetv0, a_int msaupd, a_int msaup
   const int vals[24] = {logfil, ndigit, mgetv0, msaupd, msaup2, msaitr, mseigt, msapps, msgets, mseupd, mnaupd, mnaup2,
                         mnaitr, mneigh, mnapps, mngets, mneupd, mcaupd, mcaup2, mcaitr, mceigh, mcapps, mcgets, mceupd};
   std::memcpy(g_debug.v, vals, sizeof(vals));
+  // COMMON /debug/ as the host control code sees it (trace.hpp): same 24 integers, same order (debug.h:8-16)
+  static_assert(sizeof(TraceLevels) == sizeof(vals), "TraceLevels mirrors COMMON /debug/");
+  std::memcpy(&trace_levels(), vals, sizeof(vals));
 }
 void sstats_c(void) { g_last_counters = Counters(); }
 void sstatn_c(void) { g_last_counters = Counters(); }

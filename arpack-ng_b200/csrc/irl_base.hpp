@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "hostmath.hpp"
+#include "trace.hpp"
 #include "vecops.hpp"
 
 namespace ab200 {
@@ -217,8 +218,13 @@ class IrlBase {
         }
       }
     }
+    if (trace_levels().mgetv0 > 0 && ops_->rank() == 0)  // dgetv0.f:398-401
+      trace::dvout1(rnorm_, "_getv0: B-norm of initial / restarted starting vector");
     CO_END(gv_pc_)
   }
+
+  // trace level of the step routine: msaitr (symmetric) or mnaitr (nonsymmetric)
+  virtual int aitr_trace_level() const { return 0; }
 
   // ---------------------------------------------------------------------------------------------
   // k -> k+np step extension of the factorisation
@@ -252,6 +258,9 @@ class IrlBase {
         ai_beta_ = 0;
         cnt.nrstrt++;
         ai_rstart_ = true;
+        if (aitr_trace_level() > 0 && ops_->rank() == 0) {  // dsaitr.f:398-403
+          trace::ivout1(ai_j_, "_aitr: ****** restart at step ******");
+        }
         for (ai_itry_ = 1; ai_itry_ <= 3; ++ai_itry_) {
           gv_itry_ = ai_itry_; gv_initv_ = false; gv_j_ = ai_j_;
           CO_CALL(ai_pc_, start_vector());

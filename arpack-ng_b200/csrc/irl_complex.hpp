@@ -109,6 +109,14 @@ class IrlComplex {
     iparam[8] = cnt.nopx; iparam[9] = cnt.nbx; iparam[10] = cnt.nrorth;
     *info = info_;
     if (*info == 2) *info = 3;
+    if (*info >= 0 && trace_levels().mcaupd > 0) {  // znaupd.f:603-660
+      trace::ivout1(mxiter_out_, "_naupd: Number of update iterations taken");
+      trace::ivout1(np_, "_naupd: Number of wanted \"converged\" Ritz values");
+      trace::zvout(np_, ritz(), "_naupd: The final Ritz values");
+      trace::zvout(np_, bounds(), "_naupd: Associated Ritz estimates");
+      trace::summary("Complex implicit Arnoldi update code", mxiter_out_, cnt.nopx, cnt.nbx, cnt.nrorth, cnt.nitref,
+                     cnt.nrstrt);
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -358,6 +366,8 @@ class IrlComplex {
         }
       }
     }
+    if (trace_levels().mgetv0 > 0)  // zgetv0.f:392-395
+      trace::dvout1(rnorm_, "_getv0: B-norm of initial / restarted starting vector");
     CO_END(gv_pc_)
   }
 
@@ -380,6 +390,7 @@ class IrlComplex {
         // invariant subspace: new vector orthogonal to the current basis (znaitr.f:396-440)
         ai_beta_ = 0;
         cnt.nrstrt++;
+        if (trace_levels().mcaitr > 0) trace::ivout1(ai_j_, "_naitr: ****** RESTART AT STEP ******");  // znaitr.f:397-402
         for (ai_itry_ = 1; ai_itry_ <= 3; ++ai_itry_) {
           gv_itry_ = ai_itry_; gv_initv_ = false; gv_j_ = ai_j_;
           CO_CALL(ai_pc_, start_vector());
@@ -604,6 +615,13 @@ class IrlComplex {
     for (;;) {
       iter_++;
       np_ = kplusp_ - nev_;  // znaup2.f:397
+      if (trace_levels().mcaup2 > 0) {  // znaup2.f:391-409
+        trace::ivout1(iter_, "_naup2: **** Start of major iteration number ****");
+        if (trace_levels().mcaup2 > 1) {
+          trace::ivout1(nev_, "_naup2: The length of the current Arnoldi factorization");
+          trace::ivout1(np_, "_naup2: Extend the Arnoldi factorization by");
+        }
+      }
       ai_k_ = nev_; ai_np_ = np_;
       CO_CALL(pc_, extend());
       if (ai_info_ > 0) { fail_no_factorisation(); CO_END_EARLY(pc_); }
@@ -619,6 +637,12 @@ class IrlComplex {
       nconv_ = 0;  // znaup2.f:489-497
       for (int i = 0; i < nev_; ++i)
         if (LZ::abs(bounds()[np_ + i]) <= tol_ * std::max(eps23_, LZ::abs(ritz()[np_ + i]))) nconv_++;
+      if (trace_levels().mcaup2 > 2) {  // znaup2.f:499-509
+        const int kp[3] = {nev_, np_, nconv_};
+        trace::ivout(3, kp, "_naup2: NEV, NP, NCONV are");
+        trace::zvout(kplusp_, ritz(), "_naup2: The eigenvalues of H");
+        trace::zvout(kplusp_, bounds(), "_naup2: Ritz estimates of the current NCV Ritz values");
+      }
       {
         const int nptemp = np_;
         for (int j = 0; j < nptemp; ++j)

@@ -98,6 +98,15 @@ class IrlNonsym : public IrlBase<T> {
     iparam[8] = cnt.nopx; iparam[9] = cnt.nbx; iparam[10] = cnt.nrorth;
     *info = info_;
     if (*info == 2) *info = 3;
+    if (*info >= 0 && trace_levels().mnaupd > 0 && ops_->rank() == 0) {  // dnaupd.f:630-680
+      trace::ivout1(mxiter_out_, "_naupd: Number of update iterations taken");
+      trace::ivout1(np_, "_naupd: Number of wanted \"converged\" Ritz values");
+      trace::dvout(np_, ritzr(), "_naupd: Real part of the final Ritz values");
+      trace::dvout(np_, ritzi(), "_naupd: Imaginary part of the final Ritz values");
+      trace::dvout(np_, bounds(), "_naupd: Associated Ritz estimates");
+      trace::summary("Nonsymmetric implicit Arnoldi update code", mxiter_out_, cnt.nopx, cnt.nbx, cnt.nrorth,
+                     cnt.nitref, cnt.nrstrt);
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -326,6 +335,7 @@ class IrlNonsym : public IrlBase<T> {
       if (std::fabs(H(i + 1, i)) <= std::max(ulp_ * tst1, smlnum_)) H(i + 1, i) = T(0);
     }
   }
+  int aitr_trace_level() const override { return trace_levels().mnaitr; }
   T tiny_norm() override { return unfl_; }
 
   int ritz_bounds() {
@@ -520,6 +530,13 @@ class IrlNonsym : public IrlBase<T> {
     for (;;) {
       iter_++;
       np_ = kplusp_ - nev_;  // dnaup2.f:401
+      if (trace_levels().mnaup2 > 0 && ops_->rank() == 0) {  // dnaup2.f:390-408
+        trace::ivout1(iter_, "_naup2: **** Start of major iteration number ****");
+        if (trace_levels().mnaup2 > 1) {
+          trace::ivout1(nev_, "_naup2: The length of the current Arnoldi factorization");
+          trace::ivout1(np_, "_naup2: Extend the Arnoldi factorization by");
+        }
+      }
       this->ai_k_ = nev_; this->ai_np_ = np_;
       CO_CALL(pc_, this->extend());
       if (this->ai_info_ > 0) { fail_no_factorisation(); CO_END_EARLY(pc_); }
@@ -537,6 +554,13 @@ class IrlNonsym : public IrlBase<T> {
       if (nev_ == nev0_ + 1) numcnv_ = nev0_ + 1;
       std::copy(bounds() + np_, bounds() + np_ + nev_, wrk() + 2 * np_);
       nconv_ = count_converged(nev_, ritzr() + np_, ritzi() + np_, wrk() + 2 * np_);
+      if (trace_levels().mnaup2 > 2 && ops_->rank() == 0) {  // dnaup2.f:492-505
+        const int kp[4] = {nev_, np_, numcnv_, nconv_};
+        trace::ivout(4, kp, "_naup2: NEV, NP, NUMCNV, NCONV are");
+        trace::dvout(kplusp_, ritzr(), "_naup2: Real part of the eigenvalues of H");
+        trace::dvout(kplusp_, ritzi(), "_naup2: Imaginary part of the eigenvalues of H");
+        trace::dvout(kplusp_, bounds(), "_naup2: Ritz estimates of the current NCV Ritz values");
+      }
       {
         const int nptemp = np_;
         for (int j = 0; j < nptemp; ++j)

@@ -89,6 +89,14 @@ class IrlSym : public IrlBase<T> {
     iparam[8] = cnt.nopx; iparam[9] = cnt.nbx; iparam[10] = cnt.nrorth;
     *info = info_;
     if (*info == 2) *info = 3;
+    if (*info >= 0 && trace_levels().msaupd > 0 && ops_->rank() == 0) {  // dsaupd.f:630-680
+      trace::ivout1(mxiter_out_, "_saupd: number of update iterations taken");
+      trace::ivout1(np_, "_saupd: number of \"converged\" Ritz values");
+      trace::dvout(np_, ritz(), "_saupd: final Ritz values");
+      trace::dvout(np_, bounds(), "_saupd: corresponding error bounds");
+      trace::summary("Symmetric implicit Arnoldi update code", mxiter_out_, cnt.nopx, cnt.nbx, cnt.nrorth, cnt.nitref,
+                     cnt.nrstrt);
+    }
   }
 
   int kplusp() const { return kplusp_; }
@@ -272,6 +280,7 @@ class IrlSym : public IrlBase<T> {
     H(j, 2) += scol[j - 1];
   }
   void sweep_done(int, int) override {}
+  int aitr_trace_level() const override { return trace_levels().msaitr; }
   T tiny_norm() override { return safmin_; }
 
   // Ritz values of the kplusp x kplusp tridiagonal and their error bounds rnorm*|last row|
@@ -402,6 +411,13 @@ class IrlSym : public IrlBase<T> {
     if (this->ai_info_ > 0) { fail_no_factorisation(); CO_END_EARLY(pc_); }
     for (;;) {
       iter_++;
+      if (trace_levels().msaup2 > 0 && ops_->rank() == 0) {  // dsaup2.f:404-413
+        trace::ivout1(iter_, "_saup2: **** Start of major iteration number ****");
+        if (trace_levels().msaup2 > 1) {
+          trace::ivout1(nev_, "_saup2: The length of the current Lanczos factorization");
+          trace::ivout1(np_, "_saup2: Extend the Lanczos factorization by");
+        }
+      }
       this->ai_k_ = nev_; this->ai_np_ = np_;
       CO_CALL(pc_, this->extend());
       if (this->ai_info_ > 0) { fail_no_factorisation(); CO_END_EARLY(pc_); }
@@ -416,6 +432,12 @@ class IrlSym : public IrlBase<T> {
       select_wanted(which_, be_, ishift_, nev_, np_, ritz(), bounds(), wrk());
       std::copy(bounds() + np_, bounds() + np_ + nev_, wrk() + np_);
       nconv_ = count_converged(nev_, ritz() + np_, wrk() + np_);
+      if (trace_levels().msaup2 > 2 && ops_->rank() == 0) {  // dsaup2.f:494-504
+        const int kp[3] = {nev_, np_, nconv_};
+        trace::ivout(3, kp, "_saup2: NEV, NP, NCONV are");
+        trace::dvout(kplusp_, ritz(), "_saup2: The eigenvalues of H");
+        trace::dvout(kplusp_, bounds(), "_saup2: Ritz estimates of the current NCV Ritz values");
+      }
       {
         // shifts with a zero error bound are not applied (dsaup2.f:516-522)
         const int nptemp = np_;

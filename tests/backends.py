@@ -330,6 +330,7 @@ def hostdouble_lib():
                           C.c_int, C.c_char_p, C.c_int, rt, rp, C.c_int, rp, C.c_int, c_int_p, c_int_p, rp, rp,
                           C.c_int, c_int_p]
             f.restype = None
+        L.hd_debug.argtypes = [c_int_p]
         L.hdz_new.restype = C.c_void_p
         L.hdz_new.argtypes = [C.c_int]
         L.hdz_free.argtypes = [C.c_void_p, C.c_int]
