@@ -209,7 +209,8 @@ class Oracle:
 
 
 def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
-                   dtype=np.complex128, bop=None, rvec=True, sigma=0.0, c_abi_tol=False, ishift=1, eupd=True, ldv=None):
+                   dtype=np.complex128, bop=None, rvec=True, sigma=0.0, c_abi_tol=False, ishift=1, eupd=True, ldv=None,
+                   shifts=None):
     """RCI loop around znaupd/zneupd (cnaupd/cneupd for complex64) as EXAMPLES/COMPLEX/zndrv1.f drives it.
     op(x)->y, bop(x)->y; mode 3 with bmat='G': op(x, bx) receives workd(ipntr(3)) = B x as second argument."""
     dt = np.dtype(dtype)
@@ -236,6 +237,7 @@ def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I
     tolv = rt(tol)
     aupd = self._fn(f"{p}naupd")
     nsteps = 0
+    nshift_calls = 0
     vp = lambda a: a.ctypes.data  # noqa: E731
     while True:
         if c_abi_tol:
@@ -252,10 +254,18 @@ def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I
             nsteps += 1
         elif ido.value == 2:
             workd[ipntr[1] - 1: ipntr[1] - 1 + n] = bop(workd[ipntr[0] - 1: ipntr[0] - 1 + n])
+        elif ido.value == 3 and shifts is not None:
+            # ishift = 0 (znaupd.f:168-178): iparam(8) shifts go to workl(ipntr(14)); the Ritz values of H are in
+            # workl(ipntr(6)), their estimates in workl(ipntr(8))
+            npsh = int(iparam[7])
+            workl[ipntr[13] - 1: ipntr[13] - 1 + npsh] = shifts(workl[ipntr[5] - 1: ipntr[5] - 1 + ncv].copy(),
+                                                                workl[ipntr[7] - 1: ipntr[7] - 1 + ncv].copy(), npsh)
+            nshift_calls += 1
         else:
             break
     out = Result(info=info.value, iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v.copy(),
-                 resid=res.copy(), nconv=int(iparam[4]), tol_eff=tolv.value, nsteps=nsteps)
+                 resid=res.copy(), nconv=int(iparam[4]), tol_eff=tolv.value, nsteps=nsteps,
+                 nshift_calls=nshift_calls)
     if info.value < 0 or not eupd:
         return out
     select = np.zeros(ncv, dtype=np.int32)

@@ -137,3 +137,27 @@ def test_argument_errors_and_budget_exit(backend):
     # ncv = nev + 1 passes znaupd (ncv > nev) but zneupd answers -3 (zneupd.f:360)
     r = B().solve_complex(op, n, 3, 4, "LM", tol=1e-6, mxiter=500, resid=r0)
     assert r.info in (0, 1) and (r.get("ierr", -3) == -3 or r.nconv == 0)
+
+
+def test_user_supplied_shifts_ido3():
+    """ishift = 0: znaupd returns ido = 3 and applies the iparam(8) shifts the caller stores at workl(ipntr(14))
+    (znaup2.f:661-685).  Exact shifts supplied by hand (the np leading entries of the sorted Ritz array, i.e. the unwanted
+    ones) must reproduce the wanted eigenvalues, and the host logic must follow the oracle count for count."""
+    A = complex_tridiag(100)
+    n, nev, ncv = 100, 3, 14
+    rng = np.random.default_rng(12)
+    r0 = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+
+    def shifts(ritz, bounds, npsh):
+        return ritz[:npsh]          # zngets left the unwanted values first
+    a = Oracle().solve_complex(lambda x: A @ x, n, nev, ncv, "LM", tol=1e-10, mxiter=500, resid=r0, ishift=0,
+                               shifts=shifts)
+    b = HostDouble().solve_complex(lambda x: A @ x, n, nev, ncv, "LM", tol=1e-10, mxiter=500, resid=r0, ishift=0,
+                                   shifts=shifts)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert a.nshift_calls == b.nshift_calls > 0
+    assert _counts(a) == _counts(b)
+    assert np.abs(a.d - b.d).max() <= 1e-11 * np.abs(a.d).max()
+    dense = np.linalg.eigvals(A.toarray())
+    want = dense[np.argsort(-np.abs(dense))[:nev]]
+    assert np.abs(np.sort_complex(a.d) - np.sort_complex(want)).max() <= 1e-9 * np.abs(want).max()
