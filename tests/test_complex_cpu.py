@@ -161,3 +161,31 @@ def test_user_supplied_shifts_ido3():
     dense = np.linalg.eigvals(A.toarray())
     want = dense[np.argsort(-np.abs(dense))[:nev]]
     assert np.abs(np.sort_complex(a.d) - np.sort_complex(want)).max() <= 1e-9 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostlogic"])
+def test_generalized_mode2(backend):
+    """Mode 2 (znaupd.f:100-104): OP = inv(M) A, B = M with a Hermitian positive definite M -- every inner product is
+    a B-inner product obtained through ido = 2 hand-offs.  Largest-magnitude eigenvalues of the pencil (A, M)."""
+    import scipy.linalg as sla
+    A = complex_tridiag(120)
+    n, nev, ncv = 120, 3, 16
+    off = (1.0 + 0.5j) * np.ones(n - 1) / 6.0
+    M = sp.diags([np.conj(off), np.full(n, 4.0 / 6.0), off], [-1, 0, 1]).tocsc().astype(complex)   # Hermitian, SPD
+    lu = spla.splu(M)
+    rng = np.random.default_rng(21)
+    r0 = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+    r = BACKENDS[backend]().solve_complex(lambda x: lu.solve(A @ x), n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0,
+                                          mode=2, bmat="G", bop=lambda x: M @ x)
+    assert r.info == 0 and r.ierr == 0 and r.nconv == nev and int(r.iparam[9]) > 0
+    gd = sla.eigvals(A.toarray(), M.toarray())
+    want = gd[np.argsort(-np.abs(gd))[:nev]]
+    assert np.abs(np.sort_complex(r.d) - np.sort_complex(want)).max() <= 1e-9 * np.abs(want).max()
+    Z = r.z.T
+    assert (np.linalg.norm(A @ Z - (M @ Z) * r.d[None, :], axis=0) <= 1e-7 * np.abs(r.d).max()).all()
+    # B-orthonormal Ritz vectors: z^H M z = 1
+    assert np.abs(np.einsum("in,in->n", Z.conj(), M @ Z) - 1.0).max() <= 1e-8
+    if backend == "hostlogic":
+        o = Oracle().solve_complex(lambda x: lu.solve(A @ x), n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0,
+                                   mode=2, bmat="G", bop=lambda x: M @ x)
+        assert _counts(o) == _counts(r) and int(o.iparam[9]) == int(r.iparam[9])
