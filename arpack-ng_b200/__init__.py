@@ -91,6 +91,14 @@ def lib():
         f.argtypes = [C.c_int, C.c_char_p, c_int_p, vp, vp, C.c_int, rt, rt, vp, C.c_char_p, C.c_int, C.c_char_p,
                       C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p, c_int_p, vp, vp, C.c_int, rp, c_int_p]
         f.restype = None
+        f = getattr(L, f"p{p}naupd_c")  # ICB/parpack.h:28,32
+        f.argtypes = [C.c_int, c_int_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, rt, vp, C.c_int, vp, C.c_int, c_int_p,
+                      c_int_p, vp, vp, C.c_int, rp, c_int_p]
+        f.restype = None
+    L.ab200_pzneupd_ri.argtypes = [C.c_int, C.c_int, C.c_char_p, c_int_p, vp, vp, C.c_int, C.c_double, C.c_double, vp,
+                                   C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, vp, C.c_int, vp, C.c_int,
+                                   c_int_p, c_int_p, vp, vp, C.c_int, C.POINTER(C.c_double), c_int_p]
+    L.ab200_pzneupd_ri.restype = None
     L.ab200_set_stream.argtypes = [vp]
     L.ab200_get_stream.restype = vp
     L.ab200_set_kernel_mode.argtypes = [C.c_int]
@@ -390,7 +398,7 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
 
 
 def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.complex128,
-                  bop=None, rvec=True, sigma=0.0, device="cuda", host_buffers=False, ishift=1, eupd=True):
+                  bop=None, rvec=True, sigma=0.0, device="cuda", host_buffers=False, ishift=1, eupd=True, comm=None):
     """znaupd_c/zneupd_c (cnaupd_c/cneupd_c for complex64) solve through the C-ABI, the loop of
     EXAMPLES/COMPLEX/zndrv1.f.  Device arrays (default): ``op(x, y)`` gets complex CUDA tensor views of the workd slots;
     host_buffers=True: numpy views.  Mode 3 with bmat='G': ``op(x, y, bx)`` also receives workd(ipntr(3)) at ido = 1."""
@@ -421,11 +429,16 @@ def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode
         if resid is not None:
             res.copy_(torch.as_tensor(np.asarray(resid, dtype=np_dt)))
             info[0] = 1
-    f_aupd = getattr(L, f"{p_}naupd_c")
+    # comm != None -> the PARPACK twins pznaupd_c / pzneupd_c (n = local rows, every rank calls in lock-step)
+    f_aupd = getattr(L, f"{'p' if comm is not None else ''}{p_}naupd_c")
     rwp = rwork.ctypes.data_as(C.POINTER(rt))
     cargs = (ido.ctypes.data_as(c_int_p), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(res), ncv, _addr(v), ldv,
              iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
              info.ctypes.data_as(c_int_p))
+    if comm is not None:
+        if p_ != "z":
+            raise ArpackB200Error("solve_complex(comm=...) binds pznaupd_c/pzneupd_c only (complex128)")
+        cargs = (comm,) + cargs
     nsteps = 0
     while True:
         f_aupd(*cargs)
@@ -454,11 +467,14 @@ def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode
     d = np.zeros(nev + 1, dtype=np_dt)
     workev = np.zeros(2 * ncv, dtype=np_dt)
     sg = complex(sigma)
-    getattr(L, f"ab200_{p_}neupd_ri")(int(rvec), b"A", select.ctypes.data_as(c_int_p), _addr(d), _addr(v), ldv,
-                                      rt(sg.real), rt(sg.imag), _addr(workev), bmat.encode(), n, which.encode(), nev,
-                                      rt(tol), _addr(res), ncv, _addr(v), ldv, iparam.ctypes.data_as(c_int_p),
-                                      ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
-                                      ierr.ctypes.data_as(c_int_p))
+    eargs = (int(rvec), b"A", select.ctypes.data_as(c_int_p), _addr(d), _addr(v), ldv, rt(sg.real), rt(sg.imag),
+             _addr(workev), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(res), ncv, _addr(v), ldv,
+             iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
+             ierr.ctypes.data_as(c_int_p))
+    if comm is not None:
+        L.ab200_pzneupd_ri(comm, *eargs)
+    else:
+        getattr(L, f"ab200_{p_}neupd_ri")(*eargs)
     if ierr[0] == INFO_DEVICE_ERROR:
         raise ArpackB200Error("neupd_c (complex): CUDA device error (see stderr)")
     out.update(d=d[:nev], z=v, ierr=int(ierr[0]), workl_eupd=workl.copy(), ipntr_eupd=ipntr.copy())

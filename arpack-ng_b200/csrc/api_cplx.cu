@@ -18,6 +18,7 @@
 
 namespace ab200 {
 void set_last_counters(const Counters& c);  // api.cu (stat_c)
+NcclComm* comm_from_handle(int handle);     // comm_nccl.cpp
 
 namespace {
 
@@ -25,10 +26,12 @@ constexpr int kInfoDeviceError = -9990;
 std::mutex g_mu_z;
 
 template <typename R> struct GlobalsZ {
-  static SeedState seed;   // zgetv0's SAVE'd iseed (zgetv0.f:157-162)
-  static R smlnum_first;   // znaitr/znapps SAVE'd smlnum (znaitr.f:303-317)
+  static SeedState seed;      // zgetv0's SAVE'd iseed (zgetv0.f:157-162)
+  static SeedState seed_par;  // pzgetv0's
+  static R smlnum_first;      // znaitr/znapps SAVE'd smlnum (znaitr.f:303-317)
 };
 template <typename R> SeedState GlobalsZ<R>::seed;
+template <typename R> SeedState GlobalsZ<R>::seed_par;
 template <typename R> R GlobalsZ<R>::smlnum_first = R(-1);
 
 template <typename R>
@@ -36,6 +39,7 @@ struct CtxZ {
   using Z = std::complex<R>;
   std::unique_ptr<CudaVecOpsZ<R>> ops;
   std::unique_ptr<IrlComplex<R>> slv;
+  bool par = false;
   int n = 0, ncv = 0, mode = 1;
   char bmat = 'I';
   Z *resid_u = nullptr, *v_u = nullptr, *workd_u = nullptr;
@@ -73,11 +77,17 @@ void require_device_z() {
 }
 
 template <typename R>
-CtxZ<R>* make_ctx_z(const void* key, int n, int ncv, std::complex<R>* resid, std::complex<R>* v, int ldv,
-                    std::complex<R>* workd, bool upload_all) {
+CtxZ<R>* make_ctx_z(const void* key, bool par, int comm_handle, int n, int ncv, std::complex<R>* resid,
+                    std::complex<R>* v, int ldv, std::complex<R>* workd, bool upload_all) {
   require_device_z();
   auto c = std::make_unique<CtxZ<R>>();
-  c->ops = std::make_unique<CudaVecOpsZ<R>>((cudaStream_t)ab200_get_stream());
+  NcclComm* comm = nullptr;
+  if (par) {
+    comm = comm_from_handle(comm_handle);
+    if (!comm) throw CudaError("p[cz]naupd_c: comm is not a handle returned by ab200_comm_create()");
+  }
+  c->par = par;
+  c->ops = std::make_unique<CudaVecOpsZ<R>>((cudaStream_t)ab200_get_stream(), comm);
   c->n = n;
   c->ncv = ncv;
   c->resid_u = resid; c->v_u = v; c->workd_u = workd;
@@ -109,16 +119,22 @@ CtxZ<R>* find_ctx_z(const void* key) {
 }
 
 template <typename R>
-void zaupd_entry(int* ido, const char* bmat, int n, const char* which, int nev, R* tol, std::complex<R>* resid,
+std::unique_ptr<IrlComplex<R>> make_solver_z(CtxZ<R>* c) {
+  return std::make_unique<IrlComplex<R>>(c->ops.get(), c->par ? &GlobalsZ<R>::seed_par : &GlobalsZ<R>::seed,
+                                         &GlobalsZ<R>::smlnum_first, c->par);
+}
+
+template <typename R>
+void zaupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, const char* which, int nev, R* tol, std::complex<R>* resid,
                  int ncv, std::complex<R>* v, int ldv, int* iparam, int* ipntr, std::complex<R>* workd,
                  std::complex<R>* workl, int lworkl, R* rwork, int* info) {
   try {
     CtxZ<R>* c = nullptr;
     if (*ido == 0) {
-      c = make_ctx_z<R>(workl, n, ncv, resid, v, ldv, workd, false);
+      c = make_ctx_z<R>(workl, par, comm_handle, n, ncv, resid, v, ldv, workd, false);
       c->bmat = bmat[0];
       c->mode = iparam[6];
-      c->slv = std::make_unique<IrlComplex<R>>(c->ops.get(), &GlobalsZ<R>::seed, &GlobalsZ<R>::smlnum_first);
+      c->slv = make_solver_z<R>(c);
       if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
     } else {
       c = find_ctx_z<R>(workl);
@@ -156,7 +172,7 @@ void zaupd_entry(int* ido, const char* bmat, int n, const char* which, int nev, 
 }
 
 template <typename R>
-void zeupd_entry(int rvec, const char* howmny, const int* select, std::complex<R>* d, std::complex<R>* z, int ldz,
+void zeupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const int* select, std::complex<R>* d, std::complex<R>* z, int ldz,
                  std::complex<R> sigma, std::complex<R>* workev, const char* bmat, int n, const char* which, int nev,
                  R tol, std::complex<R>* resid, int ncv, std::complex<R>* v, int ldv, int* iparam, int* ipntr,
                  std::complex<R>* workd, std::complex<R>* workl, int lworkl, R* rwork, int* info) {
@@ -165,10 +181,10 @@ void zeupd_entry(int rvec, const char* howmny, const int* select, std::complex<R
     CtxZ<R>* c = find_ctx_z<R>(workl);
     if (!(c && c->finished && c->v_u == v && c->n == n && c->ncv == ncv)) {
       // zneupd without a preceding znaupd in this process (or with other arrays): rebuild the device view
-      c = make_ctx_z<R>(workl, n, ncv, resid, v, ldv, workd, true);
+      c = make_ctx_z<R>(workl, par, comm_handle, n, ncv, resid, v, ldv, workd, true);
       c->finished = true;
     }
-    if (!c->slv) c->slv = std::make_unique<IrlComplex<R>>(c->ops.get(), &GlobalsZ<R>::seed, &GlobalsZ<R>::smlnum_first);
+    if (!c->slv) c->slv = make_solver_z<R>(c);
     c->slv->ensure_mailbox(ncv);
     // map z: alias of v, device array, or host array with an HBM mirror
     Z* zdev = nullptr;
@@ -217,6 +233,7 @@ void release_all_cplx() {
 }
 void reset_seed_cplx() {
   GlobalsZ<double>::seed = SeedState(); GlobalsZ<float>::seed = SeedState();
+  GlobalsZ<double>::seed_par = SeedState(); GlobalsZ<float>::seed_par = SeedState();
   GlobalsZ<double>::smlnum_first = -1.0; GlobalsZ<float>::smlnum_first = -1.0f;
 }
 
@@ -231,37 +248,76 @@ extern "C" {
 void znaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol, a_dcomplex* resid,
               a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,
               a_int lworkl, double* rwork, a_int* info) {
-  zaupd_entry<double>(ido, bmat, n, which, nev, &tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd,
+  zaupd_entry<double>(false, 0, ido, bmat, n, which, nev, &tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd,
                       (zd*)workl, lworkl, rwork, info);
 }
 void zneupd_c(a_int rvec, char const* howmny, a_int const* select, a_dcomplex* d, a_dcomplex* z, a_int ldz,
               a_dcomplex sigma, a_dcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
               double tol, a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
               a_dcomplex* workd, a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info) {
-  zeupd_entry<double>(rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma.re, sigma.im), (zd*)workev, bmat, n, which,
+  zeupd_entry<double>(false, 0, rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma.re, sigma.im), (zd*)workev, bmat, n, which,
                       nev, tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd, (zd*)workl, lworkl, rwork,
                       info);
 }
 void cnaupd_c(a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol, a_fcomplex* resid,
               a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd, a_fcomplex* workl,
               a_int lworkl, float* rwork, a_int* info) {
-  zaupd_entry<float>(ido, bmat, n, which, nev, &tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr, (zf*)workd,
+  zaupd_entry<float>(false, 0, ido, bmat, n, which, nev, &tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr, (zf*)workd,
                      (zf*)workl, lworkl, rwork, info);
 }
 void cneupd_c(a_int rvec, char const* howmny, a_int const* select, a_fcomplex* d, a_fcomplex* z, a_int ldz,
               a_fcomplex sigma, a_fcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev, float tol,
               a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd,
               a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info) {
-  zeupd_entry<float>(rvec, howmny, select, (zf*)d, (zf*)z, ldz, zf(sigma.re, sigma.im), (zf*)workev, bmat, n, which,
+  zeupd_entry<float>(false, 0, rvec, howmny, select, (zf*)d, (zf*)z, ldz, zf(sigma.re, sigma.im), (zf*)workev, bmat, n, which,
                      nev, tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr, (zf*)workd, (zf*)workl, lworkl, rwork,
                      info);
 }
+// ---- ICB/parpack.h:28-33 (PARPACK/SRC/MPI/icbpzn.F90, icbpcn.F90); comm = handle from ab200_comm_create ----
+void pznaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd,
+               a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info) {
+  zaupd_entry<double>(true, comm, ido, bmat, n, which, nev, &tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr,
+                      (zd*)workd, (zd*)workl, lworkl, rwork, info);
+}
+void pzneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, a_dcomplex* d, a_dcomplex* z,
+               a_int ldz, a_dcomplex sigma, a_dcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
+               double tol, a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               a_dcomplex* workd, a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info) {
+  zeupd_entry<double>(true, comm, rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma.re, sigma.im), (zd*)workev, bmat,
+                      n, which, nev, tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd, (zd*)workl, lworkl,
+                      rwork, info);
+}
+void pcnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd,
+               a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info) {
+  zaupd_entry<float>(true, comm, ido, bmat, n, which, nev, &tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr,
+                     (zf*)workd, (zf*)workl, lworkl, rwork, info);
+}
+void pcneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, a_fcomplex* d, a_fcomplex* z,
+               a_int ldz, a_fcomplex sigma, a_fcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
+               float tol, a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               a_fcomplex* workd, a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info) {
+  zeupd_entry<float>(true, comm, rvec, howmny, select, (zf*)d, (zf*)z, ldz, zf(sigma.re, sigma.im), (zf*)workev, bmat, n,
+                     which, nev, tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr, (zf*)workd, (zf*)workl, lworkl, rwork,
+                     info);
+}
+// pzneupd_c with sigma as two reals (Python ctypes)
+void ab200_pzneupd_ri(a_fint comm, a_int rvec, char const* howmny, a_int const* select, void* d, void* z, a_int ldz,
+                      double sigma_re, double sigma_im, void* workev, char const* bmat, a_int n, char const* which,
+                      a_int nev, double tol, void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr,
+                      void* workd, void* workl, a_int lworkl, double* rwork, a_int* info) {
+  zeupd_entry<double>(true, comm, rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma_re, sigma_im), (zd*)workev, bmat,
+                      n, which, nev, tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd, (zd*)workl, lworkl,
+                      rwork, info);
+}
+
 // ctypes-friendly twins of z/cneupd_c: sigma as two reals (ctypes cannot pass a C complex by value)
 void ab200_zneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* d, void* z, a_int ldz, double sigma_re,
                      double sigma_im, void* workev, char const* bmat, a_int n, char const* which, a_int nev, double tol,
                      void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr, void* workd, void* workl,
                      a_int lworkl, double* rwork, a_int* info) {
-  zeupd_entry<double>(rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma_re, sigma_im), (zd*)workev, bmat, n, which,
+  zeupd_entry<double>(false, 0, rvec, howmny, select, (zd*)d, (zd*)z, ldz, zd(sigma_re, sigma_im), (zd*)workev, bmat, n, which,
                       nev, tol, (zd*)resid, ncv, (zd*)v, ldv, iparam, ipntr, (zd*)workd, (zd*)workl, lworkl, rwork,
                       info);
 }
@@ -269,7 +325,7 @@ void ab200_cneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* 
                      float sigma_im, void* workev, char const* bmat, a_int n, char const* which, a_int nev, float tol,
                      void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr, void* workd, void* workl,
                      a_int lworkl, float* rwork, a_int* info) {
-  zeupd_entry<float>(rvec, howmny, select, (zf*)d, (zf*)z, ldz, zf(sigma_re, sigma_im), (zf*)workev, bmat, n, which,
+  zeupd_entry<float>(false, 0, rvec, howmny, select, (zf*)d, (zf*)z, ldz, zf(sigma_re, sigma_im), (zf*)workev, bmat, n, which,
                      nev, tol, (zf*)resid, ncv, (zf*)v, ldv, iparam, ipntr, (zf*)workd, (zf*)workl, lworkl, rwork,
                      info);
 }
@@ -321,14 +377,14 @@ int ab200_debug_zvq_f64(long long n, int kin, int kout, const void* v, long long
 void znaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, a_dcomplex* resid,
              a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,
              a_int* lworkl, double* rwork, a_int* info, size_t, size_t) {
-  zaupd_entry<double>(ido, bmat, *n, which, *nev, tol, (zd*)resid, *ncv, (zd*)v, *ldv, iparam, ipntr, (zd*)workd,
+  zaupd_entry<double>(false, 0, ido, bmat, *n, which, *nev, tol, (zd*)resid, *ncv, (zd*)v, *ldv, iparam, ipntr, (zd*)workd,
                       (zd*)workl, *lworkl, rwork, info);
 }
 void zneupd_(a_int* rvec, const char* howmny, a_int* select, a_dcomplex* d, a_dcomplex* z, a_int* ldz,
              a_dcomplex* sigma, a_dcomplex* workev, const char* bmat, a_int* n, const char* which, a_int* nev,
              double* tol, a_dcomplex* resid, a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr,
              a_dcomplex* workd, a_dcomplex* workl, a_int* lworkl, double* rwork, a_int* info, size_t, size_t, size_t) {
-  zeupd_entry<double>(*rvec, howmny, select, (zd*)d, (zd*)z, *ldz, zd(sigma->re, sigma->im), (zd*)workev, bmat, *n,
+  zeupd_entry<double>(false, 0, *rvec, howmny, select, (zd*)d, (zd*)z, *ldz, zd(sigma->re, sigma->im), (zd*)workev, bmat, *n,
                       which, *nev, *tol, (zd*)resid, *ncv, (zd*)v, *ldv, iparam, ipntr, (zd*)workd, (zd*)workl, *lworkl,
                       rwork, info);
 }

@@ -27,7 +27,11 @@ class IrlComplex {
   using LZ = LapackZ<R>;
 
  public:
-  IrlComplex(VecOps<Z>* ops, SeedState* seed, R* smlnum_first) : ops_(ops), seed_(seed), smlnum_first_(smlnum_first) {}
+  // parpack: the semantics of PARPACK/SRC/MPI/pzn*.f (per-rank seeds, the initial OP*x only for bmat = 'G', five
+  // start-vector refinements, eps23 with a REAL exponent, no ncv > n test, machine constants per call); the
+  // all-reduces themselves are the ops' allreduce_sum, a no-op on one rank
+  IrlComplex(VecOps<Z>* ops, SeedState* seed, R* smlnum_first, bool parpack = false)
+      : ops_(ops), seed_(seed), smlnum_first_(smlnum_first), par_(parpack) {}
 
   Counters cnt;
   const Counters& counters() const { return cnt; }
@@ -53,7 +57,7 @@ class IrlComplex {
                        which_ == Key::LI || which_ == Key::SI;
       if (n <= 0) ierr = -1;
       else if (nev <= 0) ierr = -2;
-      else if (ncv <= nev || ncv > n) ierr = -3;  // znaupd.f:467 (zneupd is stricter: ncv > nev+1)
+      else if (ncv <= nev || (!par_ && ncv > n)) ierr = -3;  // znaupd.f:467 (zneupd is stricter); pznaupd.f:481
       else if (mxiter_ <= 0) ierr = -4;
       else if (!okw) ierr = -5;
       else if (bmat != 'I' && bmat != 'G') ierr = -6;
@@ -78,13 +82,13 @@ class IrlComplex {
       ipntr[4] = ih_ + 1; ipntr[5] = iritz_ + 1; ipntr[6] = iq_ + 1; ipntr[7] = ibounds_ + 1;
       ipntr[13] = iw_ + 1;
       setup_mailbox();
-      eps23_ = eps23_of<R>(L::lamch("E"), false);
+      eps23_ = eps23_of<R>(L::lamch("E"), par_);  // pznaup2.f:277: REAL exponent
       // machine constants of znaitr/znapps (znaitr.f:303-317): smlnum from the n of the first ever call
       unfl_ = L::lamch("S");
       R ovfl = R(1) / unfl_;
       L::labad(unfl_, ovfl);
       ulp_ = L::lamch("P");
-      if (*smlnum_first_ < R(0)) *smlnum_first_ = unfl_ * (R(n) / ulp_);
+      if (par_ || *smlnum_first_ < R(0)) *smlnum_first_ = unfl_ * (R(n) / ulp_);  // pcontext: per call under PARPACK
       smlnum_ = *smlnum_first_;
       nconv_ = 0; iter_ = 0;
       initv_ = (*info != 0);
@@ -109,7 +113,7 @@ class IrlComplex {
     iparam[8] = cnt.nopx; iparam[9] = cnt.nbx; iparam[10] = cnt.nrorth;
     *info = info_;
     if (*info == 2) *info = 3;
-    if (*info >= 0 && trace_levels().mcaupd > 0) {  // znaupd.f:603-660
+    if (*info >= 0 && trace_levels().mcaupd > 0 && ops_->rank() == 0) {  // znaupd.f:603-660
       trace::ivout1(mxiter_out_, "_naupd: Number of update iterations taken");
       trace::ivout1(np_, "_naupd: Number of wanted \"converged\" Ritz values");
       trace::zvout(np_, ritz(), "_naupd: The final Ritz values");
@@ -129,7 +133,7 @@ class IrlComplex {
     const int mode = iparam[6];
     int nconv = iparam[4];
     *info = 0;
-    const R eps23 = eps23_of<R>(L::lamch("E"), false);
+    const R eps23 = eps23_of<R>(L::lamch("E"), par_);  // pzneupd.f:359
     int ierr = 0;
     const Key wk = key_of(which);
     const bool okw = wk == Key::LM || wk == Key::SM || wk == Key::LR || wk == Key::SR || wk == Key::LI || wk == Key::SI;
@@ -169,7 +173,7 @@ class IrlComplex {
         if (numcnv < nconv && LZ::abs(W[ibd + jj - 1]) <= tol * rtemp) {
           select[jj - 1] = 1;
           numcnv++;
-          if (jj > nconv) reord = true;
+          if (jj > (par_ ? nev : nconv)) reord = true;  // pzneupd.f:547 compares with nev
         }
       }
       if (numcnv != nconv) { *info = -15; return; }
@@ -183,7 +187,8 @@ class IrlComplex {
       if (reord) {
         int nconv2 = 0;
         ierr = LZ::trsen_NV(select, ncv, W + iuptri, ldh, W + invsub, ldq, W + iheig, &nconv2, workev, ncv);
-        if (nconv2 < nconv) nconv = nconv2;
+        if (par_) nconv = nconv2;  // pzneupd.f:611-615 lets ztrsen overwrite nconv
+        else if (nconv2 < nconv) nconv = nconv2;
         if (ierr == 1) { *info = 1; return; }
       }
       for (int j = 0; j < ncv; ++j) W[ihbds + j] = W[invsub + (size_t)j * ldq + ncv - 1];
@@ -252,6 +257,7 @@ class IrlComplex {
   VecOps<Z>* ops_;
   SeedState* seed_;
   R* smlnum_first_;
+  const bool par_;
   int n_ = 0, ncv_ = 0, mode_ = 1;
   char bmat_ = 'I';
   Z *resid_ = nullptr, *v_ = nullptr, *workd_ = nullptr;
@@ -309,21 +315,29 @@ class IrlComplex {
 
   bool start_vector() {
     CO_BEGIN(gv_pc_)
-    if (!seed_->inited) {  // zgetv0.f:196-202
-      seed_->iseed[0] = 1; seed_->iseed[1] = 3; seed_->iseed[2] = 5; seed_->iseed[3] = 7;
+    if (!seed_->inited) {
+      if (!par_) {  // zgetv0.f:196-202
+        seed_->iseed[0] = 1; seed_->iseed[1] = 3; seed_->iseed[2] = 5; seed_->iseed[3] = 7;
+      } else {  // pzgetv0.f:210-222, digits of 1000 + 2*rank + 1
+        int igen = 1000 + 2 * ops_->rank() + 1;
+        seed_->iseed[0] = igen / 1000; igen %= 1000;
+        seed_->iseed[1] = igen / 100;  igen %= 100;
+        seed_->iseed[2] = igen / 10;
+        seed_->iseed[3] = igen % 10;
+      }
       seed_->inited = true;
     }
     gv_ierr_ = 0;
     gv_iter_ = 0;
     if (!gv_initv_) ops_->larnv_uniform_m1_1(n_, seed_->iseed, resid_);  // zlarnv(idist = 2)
-    if (gv_itry_ == 1) {  // force the vector into range(OP) (zgetv0.f:238-245)
+    if (par_ ? (bmat_ == 'G') : (gv_itry_ == 1)) {  // force the vector into range(OP) (zgetv0.f:238-245; pzgetv0.f:249)
       cnt.nopx++;
       ops_->copy(n_, resid_, slot(1));
       ipntr_[0] = 1; ipntr_[1] = n_ + 1;
       ido_ = -1;
       CO_YIELD(gv_pc_);
       ops_->copy(n_, slot(n_ + 1), resid_);
-    } else if (bmat_ == 'G') {
+    } else if (!par_ && bmat_ == 'G') {
       ops_->copy(n_, resid_, slot(n_ + 1));
     }
     if (bmat_ == 'G') {
@@ -356,7 +370,7 @@ class IrlComplex {
         rnorm_ = fetch_norm_from_dot(mbC());
         if (rnorm_ > dgks_threshold<R>() * gv_rnorm0_) break;
         gv_iter_++;
-        if (gv_iter_ <= 1) {
+        if (gv_iter_ <= (par_ ? 5 : 1)) {  // zgetv0.f:376 ; pzgetv0.f:372
           gv_rnorm0_ = rnorm_;
         } else {
           ops_->zero(n_, resid_);
@@ -366,7 +380,7 @@ class IrlComplex {
         }
       }
     }
-    if (trace_levels().mgetv0 > 0)  // zgetv0.f:392-395
+    if (trace_levels().mgetv0 > 0 && ops_->rank() == 0)  // zgetv0.f:392-395
       trace::dvout1(rnorm_, "_getv0: B-norm of initial / restarted starting vector");
     CO_END(gv_pc_)
   }
@@ -390,7 +404,7 @@ class IrlComplex {
         // invariant subspace: new vector orthogonal to the current basis (znaitr.f:396-440)
         ai_beta_ = 0;
         cnt.nrstrt++;
-        if (trace_levels().mcaitr > 0) trace::ivout1(ai_j_, "_naitr: ****** RESTART AT STEP ******");  // znaitr.f:397-402
+        if (trace_levels().mcaitr > 0 && ops_->rank() == 0) trace::ivout1(ai_j_, "_naitr: ****** RESTART AT STEP ******");  // znaitr.f:397-402
         for (ai_itry_ = 1; ai_itry_ <= 3; ++ai_itry_) {
           gv_itry_ = ai_itry_; gv_initv_ = false; gv_j_ = ai_j_;
           CO_CALL(ai_pc_, start_vector());
@@ -615,7 +629,7 @@ class IrlComplex {
     for (;;) {
       iter_++;
       np_ = kplusp_ - nev_;  // znaup2.f:397
-      if (trace_levels().mcaup2 > 0) {  // znaup2.f:391-409
+      if (trace_levels().mcaup2 > 0 && ops_->rank() == 0) {  // znaup2.f:391-409
         trace::ivout1(iter_, "_naup2: **** Start of major iteration number ****");
         if (trace_levels().mcaup2 > 1) {
           trace::ivout1(nev_, "_naup2: The length of the current Arnoldi factorization");
@@ -637,7 +651,7 @@ class IrlComplex {
       nconv_ = 0;  // znaup2.f:489-497
       for (int i = 0; i < nev_; ++i)
         if (LZ::abs(bounds()[np_ + i]) <= tol_ * std::max(eps23_, LZ::abs(ritz()[np_ + i]))) nconv_++;
-      if (trace_levels().mcaup2 > 2) {  // znaup2.f:499-509
+      if (trace_levels().mcaup2 > 2 && ops_->rank() == 0) {  // znaup2.f:499-509
         const int kp[3] = {nev_, np_, nconv_};
         trace::ivout(3, kp, "_naup2: NEV, NP, NCONV are");
         trace::zvout(kplusp_, ritz(), "_naup2: The eigenvalues of H");

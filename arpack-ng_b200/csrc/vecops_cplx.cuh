@@ -14,7 +14,7 @@ template <typename R>
 class CudaVecOpsZ final : public VecOps<std::complex<R>> {
  public:
   using T = std::complex<R>;
-  explicit CudaVecOpsZ(cudaStream_t stream) : real_(stream, nullptr), stream_(stream) {
+  explicit CudaVecOpsZ(cudaStream_t stream, NcclComm* comm = nullptr) : real_(stream, comm), stream_(stream) {
     int dev = 0;
     AB200_CUDA_CHECK(cudaGetDevice(&dev));
     AB200_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
@@ -37,9 +37,10 @@ class CudaVecOpsZ final : public VecOps<std::complex<R>> {
   T* mailbox(size_t count) override { return reinterpret_cast<T*>(real_.mailbox(2 * count)); }
   void fetch(T* host_dst, const T* mb, size_t count) override { real_.fetch((R*)host_dst, (const R*)mb, 2 * count); }
   void post(T* mb, const T* host_src, size_t count) override { real_.post((R*)mb, (const R*)host_src, 2 * count); }
-  void allreduce_sum(T*, size_t) override {}  // sequential entry points only (no pznaupd yet)
-  int rank() const override { return 0; }
-  int nranks() const override { return 1; }
+  // PARPACK: MPI_ALLREDUCE(MPI_DOUBLE_COMPLEX, SUM) of pznaitr.f:437-449 == a sum of 2*count reals, in stream order
+  void allreduce_sum(T* mb, size_t count) override { real_.allreduce_sum((R*)mb, 2 * count); }
+  int rank() const override { return real_.rank(); }
+  int nranks() const override { return real_.nranks(); }
 
   void copy(int64_t n, const T* x, T* y) override { real_.copy(2 * n, (const R*)x, (R*)y); }
   void zero(int64_t n, T* x) override { real_.zero(2 * n, (R*)x); }

@@ -94,6 +94,27 @@ void ab200_cneupd_ri(a_int rvec, char const* howmny, a_int const* select, void* 
                      float sigma_im, void* workev, char const* bmat, a_int n, char const* which, a_int nev, float tol,
                      void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr, void* workd, void* workl,
                      a_int lworkl, float* rwork, a_int* info);
+/* PARPACK twins, ICB/parpack.h:28-33 (PARPACK/SRC/MPI/pznaupd.f, pzneupd.f, pcnaupd.f, pcneupd.f): n = local rows,
+ * comm = handle from ab200_comm_create(); the MPI_ALLREDUCEs of pznaitr.f:437-449, pzgetv0.f:322-328 and pdznorm2.f
+ * are all-reduces of the device mailbox on the solve's stream. */
+void pznaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, double tol,
+               a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd,
+               a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info);
+void pzneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, a_dcomplex* d, a_dcomplex* z,
+               a_int ldz, a_dcomplex sigma, a_dcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
+               double tol, a_dcomplex* resid, a_int ncv, a_dcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               a_dcomplex* workd, a_dcomplex* workl, a_int lworkl, double* rwork, a_int* info);
+void pcnaupd_c(a_fint comm, a_int* ido, char const* bmat, a_int n, char const* which, a_int nev, float tol,
+               a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr, a_fcomplex* workd,
+               a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info);
+void pcneupd_c(a_fint comm, a_int rvec, char const* howmny, a_int const* select, a_fcomplex* d, a_fcomplex* z,
+               a_int ldz, a_fcomplex sigma, a_fcomplex* workev, char const* bmat, a_int n, char const* which, a_int nev,
+               float tol, a_fcomplex* resid, a_int ncv, a_fcomplex* v, a_int ldv, a_int* iparam, a_int* ipntr,
+               a_fcomplex* workd, a_fcomplex* workl, a_int lworkl, float* rwork, a_int* info);
+void ab200_pzneupd_ri(a_fint comm, a_int rvec, char const* howmny, a_int const* select, void* d, void* z, a_int ldz,
+                      double sigma_re, double sigma_im, void* workev, char const* bmat, a_int n, char const* which,
+                      a_int nev, double tol, void* resid, a_int ncv, void* v, a_int ldv, a_int* iparam, a_int* ipntr,
+                      void* workd, void* workl, a_int lworkl, double* rwork, a_int* info);
 /* legacy Fortran ABI of the same (SRC/znaupd.f:384, zneupd.f:248) */
 void znaupd_(a_int* ido, const char* bmat, a_int* n, const char* which, a_int* nev, double* tol, a_dcomplex* resid,
              a_int* ncv, a_dcomplex* v, a_int* ldv, a_int* iparam, a_int* ipntr, a_dcomplex* workd, a_dcomplex* workl,

@@ -345,6 +345,7 @@ def hostdouble_lib():
         L.hdz_new.argtypes = [C.c_int]
         L.hdz_free.argtypes = [C.c_void_p, C.c_int]
         L.hdz_stats.argtypes = [C.c_void_p, C.c_int, c_int_p]
+        L.hdz_set_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ALLREDUCE_FN]
         for p, rp, rt in (("z", c_dbl_p, C.c_double), ("c", c_flt_p, C.c_float)):
             vp = C.c_void_p
             f = getattr(L, f"hd_{p}naupd")
@@ -376,6 +377,8 @@ class HostDouble(Oracle):
             self._cb = _make_allreduce_cb(allreduce)
             for isd, pr in self._procs.items():
                 self.L.hd_set_comm(pr, int(isd), rank, nranks, self._cb)
+            for isd, pr in self._procs_z.items():
+                self.L.hdz_set_comm(pr, int(isd), rank, nranks, self._cb)
 
     def __del__(self):
         try:

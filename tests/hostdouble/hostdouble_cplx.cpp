@@ -19,10 +19,14 @@ namespace {
 
 using namespace ab200;
 
+typedef void (*allreduce_fn)(void* user, void* buf, int count, int is_double, int op);
+
 template <typename R>
 struct HostVecOpsZ final : VecOps<std::complex<R>> {
   using T = std::complex<R>;
   std::vector<T> mb_;
+  int rank_ = 0, nranks_ = 1;
+  allreduce_fn ar_ = nullptr;
 
   T* alloc(size_t c) override { return (T*)std::calloc(c ? c : 1, sizeof(T)); }
   void release(T* p) override { std::free(p); }
@@ -42,9 +46,11 @@ struct HostVecOpsZ final : VecOps<std::complex<R>> {
   }
   void fetch(T* h, const T* mb, size_t c) override { std::memcpy(h, mb, sizeof(T) * c); }
   void post(T* mb, const T* h, size_t c) override { std::memcpy(mb, h, sizeof(T) * c); }
-  void allreduce_sum(T*, size_t) override {}
-  int rank() const override { return 0; }
-  int nranks() const override { return 1; }
+  void allreduce_sum(T* mb, size_t c) override {  // complex sum == sum of 2c reals
+    if (ar_ && c) ar_(nullptr, mb, (int)(2 * c), sizeof(R) == 8, 0);
+  }
+  int rank() const override { return rank_; }
+  int nranks() const override { return nranks_; }
 
   void copy(int64_t n, const T* x, T* y) override {
     if (x != y) std::memmove(y, x, sizeof(T) * (size_t)n);
@@ -153,6 +159,7 @@ struct ProcZ {
   HostVecOpsZ<R> ops;
   SeedState seed;
   R smlnum_first = R(-1);
+  bool par = false;
   std::unique_ptr<IrlComplex<R>> slv;
 };
 
@@ -165,6 +172,10 @@ void hdz_free(void* p, int is_double) {
   if (is_double) delete (ProcZ<double>*)p;
   else delete (ProcZ<float>*)p;
 }
+void hdz_set_comm(void* p, int is_double, int rank, int nranks, allreduce_fn fn) {
+  if (is_double) { auto* q = (ProcZ<double>*)p; q->par = true; q->ops.rank_ = rank; q->ops.nranks_ = nranks; q->ops.ar_ = fn; }
+  else { auto* q = (ProcZ<float>*)p; q->par = true; q->ops.rank_ = rank; q->ops.nranks_ = nranks; q->ops.ar_ = fn; }
+}
 void hdz_stats(void* p, int is_double, int* out5) {
   const Counters* c = is_double ? &((ProcZ<double>*)p)->slv->counters() : &((ProcZ<float>*)p)->slv->counters();
   out5[0] = c->nopx; out5[1] = c->nbx; out5[2] = c->nrorth; out5[3] = c->nitref; out5[4] = c->nrstrt;
@@ -175,7 +186,7 @@ void hdz_stats(void* p, int is_double, int* out5) {
             void* v, int ldv, int* iparam, int* ipntr, void* workd, void* workl, int lworkl, R* rwork, int* info) { \
     using Z = std::complex<R>;                                                                                     \
     auto* q = (ProcZ<R>*)p;                                                                                        \
-    if (*ido == 0) q->slv.reset(new IrlComplex<R>(&q->ops, &q->seed, &q->smlnum_first));                           \
+    if (*ido == 0) q->slv.reset(new IrlComplex<R>(&q->ops, &q->seed, &q->smlnum_first, q->par));                           \
     q->slv->aupd(ido, bmat[0], n, which, nev, tol, (Z*)resid, ncv, (Z*)v, ldv, iparam, ipntr, (Z*)workd,           \
                  (Z*)workl, lworkl, rwork, info);                                                                  \
   }
@@ -189,7 +200,7 @@ HDZ_AUPD(hd_cnaupd, float)
             int* info) {                                                                                           \
     using Z = std::complex<R>;                                                                                     \
     auto* q = (ProcZ<R>*)p;                                                                                        \
-    if (!q->slv) q->slv.reset(new IrlComplex<R>(&q->ops, &q->seed, &q->smlnum_first));                             \
+    if (!q->slv) q->slv.reset(new IrlComplex<R>(&q->ops, &q->seed, &q->smlnum_first, q->par));                             \
     q->slv->ensure_mailbox(ncv);                                                                                   \
     q->slv->eupd(rvec != 0, howmny[0], select, (Z*)d, (Z*)z, ldz, Z(sre, sim), (Z*)workev, bmat[0], n, which,      \
                  nev, tol, (Z*)resid, ncv, (Z*)v, ldv, iparam, ipntr, (Z*)workd, (Z*)workl, lworkl, rwork, info);  \

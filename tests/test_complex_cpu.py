@@ -189,3 +189,68 @@ def test_generalized_mode2(backend):
         o = Oracle().solve_complex(lambda x: lu.solve(A @ x), n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0,
                                    mode=2, bmat="G", bop=lambda x: M @ x)
         assert _counts(o) == _counts(r) and int(o.iparam[9]) == int(r.iparam[9])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PARPACK twins pznaupd/pzneupd on P logical ranks (no MPI in the image: threads + a barrier all-reduce)
+# ---------------------------------------------------------------------------------------------------------------
+from test_oracle_golden import LogicalRanks, split_rows  # noqa: E402
+
+
+@pytest.mark.parametrize("backend", ["oracle", "hostlogic"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_icb_parpack_c_zn_known_answer(backend, nranks):
+    """PARPACK/TESTS/MPI/icb_parpack_c.c:104-190: pznaupd_c/pzneupd_c on diag((i+1)(1+i)), i < 1000, rows split over
+    the ranks, nev=9, ncv=19, 'LM', tol=1e-6, rvec=0 -> d[i] = (992+i)(1+i) on every rank within 1e-5."""
+    N, nev, ncv = 1000, 9, 19
+    cnts, offs = split_rows(N, nranks)
+    world = LogicalRanks(nranks)
+
+    def rank_main(r, ar):
+        diag = np.arange(offs[r] + 1, offs[r + 1] + 1) * (1 + 1j)
+        return BACKENDS[backend](rank=r, nranks=nranks, allreduce=ar).solve_complex(
+            lambda x: diag * x, cnts[r], nev, ncv, "LM", tol=1e-6, mxiter=10 * N, rvec=False, c_abi_tol=True)
+    res = world.run(rank_main)
+    want = (N - (nev - 1) + np.arange(nev)) * (1 + 1j)
+    for r in res:
+        assert r.info == 0 and r.ierr == 0 and r.nconv >= nev
+        assert np.abs(r.d.real - want.real).max() <= 1e-5 and np.abs(r.d.imag - want.imag).max() <= 1e-5
+    assert all(_counts(r) == _counts(res[0]) for r in res)       # replicated host state: identical on every rank
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_parpack_complex_semantics_match_oracle(nranks):
+    """pznaupd/pzneupd path of the host logic (per-rank zlarnv seeds, no initial OP*x for bmat = 'I', all-reduced
+    coefficients and norms, eps23 with a REAL exponent) against the oracle's PARPACK mode on P logical ranks: same
+    path, same eigenvalues, eigenvector rows of the right operator."""
+    A = complex_tridiag(180)
+    n, nev, ncv = A.shape[0], 4, 18
+    cnts, offs = split_rows(n, nranks)
+
+    def run(cls, use_r0):
+        world = LogicalRanks(nranks)
+        rng = np.random.default_rng(17)
+        r0 = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
+
+        def rank_main(r, ar):
+            def op(x):
+                # "halo exchange": gather the full vector through the all-reduce callback (re and im parts)
+                full = np.zeros(2 * n)
+                full[2 * offs[r]:2 * offs[r + 1]] = x.view(np.float64)
+                full = ar(full, 0).view(np.complex128)
+                return (A @ full)[offs[r]:offs[r + 1]]
+            return cls(rank=r, nranks=nranks, allreduce=ar).solve_complex(
+                op, cnts[r], nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0[offs[r]:offs[r + 1]] if use_r0 else None)
+        return world.run(rank_main)
+    for use_r0 in (True, False):
+        a, b = run(HostDouble, use_r0), run(Oracle, use_r0)
+        for ra, rb in zip(a, b):
+            assert ra.info == rb.info == 0 and ra.ierr == rb.ierr == 0
+            assert _counts(ra) == _counts(rb)
+            assert np.abs(ra.d - rb.d).max() <= 1e-10 * np.abs(rb.d).max()
+        # the local eigenvector blocks assemble to eigenvectors of A
+        Z = np.concatenate([ra.z for ra in a], axis=1).T          # n x nev
+        assert (np.linalg.norm(A @ Z - Z * a[0].d[None, :], axis=0) <= 1e-7 * np.abs(a[0].d).max()).all()
+        dense = np.linalg.eigvals(A.toarray())
+        want = dense[np.argsort(-np.abs(dense))[:nev]]
+        assert np.abs(np.sort_complex(a[0].d) - np.sort_complex(want)).max() <= 1e-9 * np.abs(want).max()
