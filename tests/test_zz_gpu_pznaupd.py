@@ -3,9 +3,9 @@ PARPACK/SRC/MPI/pzn*.f -- per-rank zlarnv seed, no initial OP*x for bmat = 'I', 
 plumbing of the complex mailbox) against the oracle's PARPACK mode and the known answer of
 PARPACK/TESTS/MPI/icb_parpack_c.c:104-190.
 
-Sorted last on purpose: these entry points were added after the round's GPU budget was spent, so the GPU run of this
-file has not been observed yet.  The CPU side of the same path (oracle and host logic on 2 and 3 logical ranks) is
-covered by tests/test_complex_cpu.py; the kernels are those of the sequential complex path."""
+The CPU side of the same path (oracle and host logic on 2 and 3 logical ranks) is covered by
+tests/test_complex_cpu.py; the kernels are those of the sequential complex path.  Observed passing on a B200 with a
+1-rank communicator; a multi-rank GPU run has not been made yet."""
 import os
 
 import numpy as np
@@ -13,9 +13,7 @@ import pytest
 
 from backends import Oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="pznaupd_c on hardware not yet observed (added after the round's "
-                                                     "GPU budget was spent); CPU logical-rank tests cover the logic")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
