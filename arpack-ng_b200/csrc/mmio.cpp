@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -26,14 +27,19 @@
 
 namespace {
 
-struct Triplets {
+template <typename V>
+struct TripletsT {
   long long n = 0, m = 0;
   std::vector<long long> i, j;
-  std::vector<double> v;
+  std::vector<V> v;
 };
+using Triplets = TripletsT<double>;
 
-// returns 0, or 1 (cannot open), 2 (bad header), 3 (bad body line), 4 (index out of range)
-int read_triplets(const char* path, Triplets& t, long long* bad_line) {
+// returns 0, or 1 (cannot open), 2 (bad header), 3 (bad body line), 4 (index out of range).  V = double reads
+// "i j value"; V = std::complex<double> reads "i j (re, im)" -- the stream extraction the reference's reader uses for
+// its complex instantiation (arpackSolver.hpp:398-400), which also accepts "(re)" and a bare real.
+template <typename V>
+int read_triplets(const char* path, TripletsT<V>& t, long long* bad_line) {
   std::ifstream inp(path);
   if (!inp) return 1;
   std::string line;
@@ -55,7 +61,7 @@ int read_triplets(const char* path, Triplets& t, long long* bad_line) {
       have_header = true;
     } else {
       long long k = 0, l = 0;
-      double val = 0.0;
+      V val = V(0);
       ss >> k >> l >> val;
       if (!ss) { if (bad_line) *bad_line = lineno; return 3; }
       t.i.push_back(k);
@@ -77,14 +83,11 @@ int read_triplets(const char* path, Triplets& t, long long* bad_line) {
   return 0;
 }
 
-}  // namespace
-
-extern "C" {
-
-int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
-                      double** val_host) {
+template <typename V>
+int mm_read_csr_t(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
+                  V** val_host) {
   if (!path || !nrows || !ncols || !nnz || !rowptr_host || !col_host || !val_host) return -1;
-  Triplets t;
+  TripletsT<V> t;
   long long bad = 0;
   const int rc = read_triplets(path, t, &bad);
   if (rc != 0) {
@@ -99,7 +102,7 @@ int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, 
   for (size_t k = 0; k < nz; ++k) start[(size_t)t.i[k] + 1]++;
   for (long long r = 0; r < t.n; ++r) start[(size_t)r + 1] += start[(size_t)r];
   std::vector<int> cj(nz);
-  std::vector<double> cv(nz);
+  std::vector<V> cv(nz);
   {
     std::vector<long long> fill(start.begin(), start.end() - 1);
     for (size_t k = 0; k < nz; ++k) {
@@ -110,10 +113,10 @@ int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, 
   }
   int* rp = (int*)std::malloc(sizeof(int) * ((size_t)t.n + 1));
   int* co = (int*)std::malloc(sizeof(int) * (nz ? nz : 1));
-  double* va = (double*)std::malloc(sizeof(double) * (nz ? nz : 1));
+  V* va = (V*)std::malloc(sizeof(V) * (nz ? nz : 1));
   if (!rp || !co || !va) { std::free(rp); std::free(co); std::free(va); return 6; }
   long long out = 0;
-  std::vector<std::pair<int, double>> row;
+  std::vector<std::pair<int, V>> row;
   for (long long r = 0; r < t.n; ++r) {
     rp[r] = (int)out;
     row.clear();
@@ -137,6 +140,22 @@ int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, 
   *col_host = co;
   *val_host = va;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
+                      double** val_host) {
+  return mm_read_csr_t<double>(path, nrows, ncols, nnz, rowptr_host, col_host, val_host);
+}
+// complex coordinate files (EXAMPLES/MATRIX_MARKET/Az.mtx, Bz.mtx: "i j (re, im)"); val_host is interleaved (re, im)
+int ab200_mm_read_csr_z(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
+                        double** val_host) {
+  std::complex<double>* zv = nullptr;
+  const int rc = mm_read_csr_t<std::complex<double>>(path, nrows, ncols, nnz, rowptr_host, col_host, &zv);
+  if (val_host) *val_host = reinterpret_cast<double*>(zv);
+  return rc;
 }
 
 void ab200_mm_free(void* p) { std::free(p); }

@@ -287,6 +287,10 @@ int ab200_residuals_f64(int n, const int* rowptr, const int* col, const double* 
  * Returns 0, 1 cannot open, 2 bad header, 3 bad line, 4 index out of range, 5 too large for int32, 6 out of memory. */
 int ab200_mm_read_csr(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
                       double** val_host);
+/* the same for complex coordinate files ("i j (re, im)", the reference's Az.mtx / Bz.mtx; arpackSolver.hpp:398-400 reads
+ * the value with the stream extraction of std::complex): val_host holds nnz interleaved (re, im) pairs */
+int ab200_mm_read_csr_z(const char* path, int* nrows, int* ncols, long long* nnz, int** rowptr_host, int** col_host,
+                        double** val_host);
 void ab200_mm_free(void* p);
 /* the --restart dump of arpackSolver.hpp:664-704: "count" then one value per line; load fails (2) on a count
  * mismatch and, with allow_zero = 0, replaces |value| < 1e-6 by machine epsilon (resid must not be zero) */

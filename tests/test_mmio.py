@@ -107,3 +107,39 @@ def test_restart_files_roundtrip_and_zero_guard(L, tmp_path):
     assert np.array_equal(y, np.array([1.25, eps, eps, 2.0e10, -7.125]))
     assert L.ab200_restart_load_f64(p, 6, y.ctypes.data, 1) == 2      # "bad dim - restart KO"
     assert L.ab200_restart_load_f64(str(tmp_path / "nope").encode(), 5, y.ctypes.data, 1) == 1
+
+
+def test_complex_coordinate_files(L, tmp_path):
+    """Complex files in the style of the reference's fixtures EXAMPLES/MATRIX_MARKET/Az.mtx / Bz.mtx: 0-based, no nnz,
+    values written "(re, im)" with blanks inside the parentheses; also "(re)" and a bare real, which the stream
+    extraction of std::complex the reference uses (arpackSolver.hpp:398-400) accepts; duplicates are summed."""
+    L.ab200_mm_read_csr_z.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                                      C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
+                                      C.POINTER(C.POINTER(C.c_double))]
+    p = tmp_path / "Az.mtx"
+    p.write_text("%% MatrixMarket matrix coordinate complex general\n% 0-based without (optional) nnz\n%\n4 4\n\n"
+                 "0  0  (  1., 0.)\n1  1  (200., -3.5)\n2  2  (200.)\n3  3  7.25\n"
+                 "1  0  (-100., 2.)\n0  1  ( -100.,2. )\n1  0  (0.5, 0.5)\n3  0  (0., -1.)\n")
+    n, m, nnz = C.c_int(), C.c_int(), C.c_longlong()
+    rp, co, va = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+    assert L.ab200_mm_read_csr_z(str(p).encode(), C.byref(n), C.byref(m), C.byref(nnz), C.byref(rp), C.byref(co),
+                                 C.byref(va)) == 0
+    vals = np.ctypeslib.as_array(va, (2 * nnz.value,)).copy().view(np.complex128)
+    A = sp.csr_matrix((vals, np.ctypeslib.as_array(co, (nnz.value,)).copy(),
+                       np.ctypeslib.as_array(rp, (n.value + 1,)).copy()), shape=(n.value, m.value)).toarray()
+    for q in (rp, co, va):
+        L.ab200_mm_free(q)
+    want = np.zeros((4, 4), dtype=complex)
+    want[0, 0] = 1.0
+    want[1, 1] = 200 - 3.5j
+    want[2, 2] = 200.0
+    want[3, 3] = 7.25
+    want[1, 0] = (-100 + 2j) + (0.5 + 0.5j)
+    want[0, 1] = -100 + 2j
+    want[3, 0] = -1j
+    assert (n.value, m.value, nnz.value) == (4, 4, 7)
+    assert np.array_equal(A, want)
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("2 2\n0 0 (1., \n")
+    assert L.ab200_mm_read_csr_z(str(bad).encode(), C.byref(n), C.byref(m), C.byref(nnz), C.byref(rp), C.byref(co),
+                                 C.byref(va)) == 3
