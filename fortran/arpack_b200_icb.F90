@@ -117,6 +117,30 @@ module arpack_b200_icb
       real(c_double) :: d(*), z(ldz, *), resid(*), v(ldv, *), workd(*), workl(*)
     end subroutine pdseupd_c
 
+    ! ---- ICB/parpack.h:22-23 (PARPACK/SRC/MPI/icbpdn.F90) ----
+    subroutine pdnaupd_c(comm, ido, bmat, n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, &
+                         lworkl, info) bind(c, name="pdnaupd_c")
+      import :: c_int, c_double, c_char
+      integer(c_int), value :: comm
+      integer(c_int), intent(inout) :: ido, info
+      character(kind=c_char), intent(in) :: bmat(*), which(*)
+      integer(c_int), value :: n, nev, ncv, ldv, lworkl
+      real(c_double), value :: tol
+      real(c_double) :: resid(*), v(ldv, *), workd(*), workl(*)
+      integer(c_int) :: iparam(11), ipntr(14)
+    end subroutine pdnaupd_c
+
+    subroutine pdneupd_c(comm, rvec, howmny, select, dr, di, z, ldz, sigmar, sigmai, workev, bmat, n, which, nev, &
+                         tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl, lworkl, info) bind(c, name="pdneupd_c")
+      import :: c_int, c_double, c_char
+      integer(c_int), value :: comm, rvec, ldz, n, nev, ncv, ldv, lworkl
+      character(kind=c_char), intent(in) :: howmny(*), bmat(*), which(*)
+      integer(c_int) :: select(*), iparam(11), ipntr(14)
+      integer(c_int), intent(inout) :: info
+      real(c_double), value :: sigmar, sigmai, tol
+      real(c_double) :: dr(*), di(*), z(ldz, *), workev(*), resid(*), v(ldv, *), workd(*), workl(*)
+    end subroutine pdneupd_c
+
     ! ---- extensions of the GPU library (include/arpack_b200.h) ----
     ! stream on which the library enqueues its kernels and on which the ido = -1/1/2 hand-off is ordered
     function ab200_get_stream() bind(c, name="ab200_get_stream") result(stream)
