@@ -22,6 +22,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_v
 ZCMD="python tools/complex_probe.py --restarts 2"
 timeout 120 $ZCMD > /dev/null 2>&1 || exit 3
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_zdots|k_zupdate|k_zvq" -s 60 -c 6 -f -o gpurun_out/${tag}_prof_cplx $ZCMD > gpurun_out/${tag}_ncu_cplx.log 2>&1
-python tools/ncu_summarize.py gpurun_out/${tag}_prof_vq.ncu-rep > gpurun_out/${tag}_ncu_vq_summary.json 2>/dev/null
-python tools/ncu_summarize.py gpurun_out/${tag}_prof_cplx.ncu-rep > gpurun_out/${tag}_ncu_cplx_summary.json 2>/dev/null
+python tools/ncu_summarize.py gpurun_out/${tag}_prof_vq.ncu-rep gpurun_out/${tag}_ncu_vq_summary.json
+python tools/ncu_summarize.py gpurun_out/${tag}_prof_cplx.ncu-rep gpurun_out/${tag}_ncu_cplx_summary.json
 ls -la gpurun_out | tail -20
