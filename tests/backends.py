@@ -121,7 +121,7 @@ class Oracle:
 
     def solve(self, op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
               dtype=np.float64, bop=None, rvec=True, sigma=0.0, sigmai=0.0, c_abi_tol=False, ishift=1,
-              eupd=True, ldv=None):
+              eupd=True, ldv=None, howmny="A"):
         """RCI loop exactly as EXAMPLES/SIMPLE/dssimp.f:302-324 drives it.
         op(x)->y, bop(x)->y.  c_abi_tol=True mimics the *_c entry points (tol by value, see SRC/icbads.F90)."""
         L = self.L
@@ -189,7 +189,7 @@ class Oracle:
             d = np.zeros(nev, dtype=dt)
             z = np.zeros((nev, n), dtype=dt)
             L_ = self._fn(f"{p}seupd")
-            L_(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), _p(d, rp), _p(z, rp), n, rt(sigma), bmat.encode(), n,
+            L_(*self._ctxargs(p), int(rvec), howmny.encode(), _p(select, c_int_p), _p(d, rp), _p(z, rp), n, rt(sigma), bmat.encode(), n,
                which.encode(), nev, rt(tol_e), _p(res, rp), ncv, _p(v, rp), ldv, _p(iparam, c_int_p),
                _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl, C.byref(ierr))
             out.update(d=d, z=z, ierr=ierr.value)
@@ -199,7 +199,7 @@ class Oracle:
             z = np.zeros((max(ncv, nev + 1), n), dtype=dt)  # dneupd.f:893 treats Z as n x ncv
             workev = np.zeros(3 * ncv, dtype=dt)
             L_ = self._fn(f"{p}neupd")
-            L_(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
+            L_(*self._ctxargs(p), int(rvec), howmny.encode(), _p(select, c_int_p), _p(dr, rp), _p(di, rp), _p(z, rp), n, rt(sigma),
                rt(sigmai), _p(workev, rp), bmat.encode(), n, which.encode(), nev, rt(tol_e), _p(res, rp), ncv,
                _p(v, rp), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), _p(workd, rp), _p(workl, rp), lworkl,
                C.byref(ierr))
@@ -210,7 +210,7 @@ class Oracle:
 
 def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None,
                    dtype=np.complex128, bop=None, rvec=True, sigma=0.0, c_abi_tol=False, ishift=1, eupd=True, ldv=None,
-                   shifts=None):
+                   shifts=None, howmny="A"):
     """RCI loop around znaupd/zneupd (cnaupd/cneupd for complex64) as EXAMPLES/COMPLEX/zndrv1.f drives it.
     op(x)->y, bop(x)->y; mode 3 with bmat='G': op(x, bx) receives workd(ipntr(3)) = B x as second argument."""
     dt = np.dtype(dtype)
@@ -275,7 +275,7 @@ def _solve_complex(self, op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I
     z = np.zeros((nev, n), dtype=dt)
     workev = np.zeros(2 * ncv, dtype=dt)
     sg = complex(sigma)
-    self._fn(f"{p}neupd_ri")(*self._ctxargs(p), int(rvec), b"A", _p(select, c_int_p), vp(d), vp(z), n, rt(sg.real),
+    self._fn(f"{p}neupd_ri")(*self._ctxargs(p), int(rvec), howmny.encode(), _p(select, c_int_p), vp(d), vp(z), n, rt(sg.real),
                              rt(sg.imag), vp(workev), bmat.encode(), n, which.encode(), nev, rt(tol_e), vp(res), ncv,
                              vp(v), ldv, _p(iparam, c_int_p), _p(ipntr, c_int_p), vp(workd), vp(workl), lworkl,
                              _p(rwork, rp), C.byref(ierr))
