@@ -59,3 +59,26 @@ def test_zneupd_schur_vectors(backend):
         o = Oracle().solve_complex(lambda x: A @ x, n, nev, ncv, "LM", tol=1e-10, mxiter=3000, resid=r0, howmny="P")
         assert (o.nconv, int(o.iparam[2]), int(o.iparam[8])) == (r.nconv, int(r.iparam[2]), int(r.iparam[8]))
         assert np.abs(np.abs(o.z[:k]) - np.abs(r.z[:k])).max() <= 1e-8
+
+
+@pytest.mark.parametrize("family", ["sym", "nonsym", "cplx"])
+def test_zero_start_vector_exits_with_info_minus_9(family):
+    """info = -9 (dsaupd.f:263, dsaup2.f:334-343, dnaup2.f:324-331, znaup2.f:326-333): a zero start vector -- given by
+    the caller or produced by OP -- ends the solve at once; what iparam(3)/iparam(5) hold then differs between the
+    families (label 1100 vs 1200 of *aup2) and must be what the oracle leaves there."""
+    from problems import laplace2d
+    n = 42
+    A = {"sym": laplace2d(7, 6).toarray(), "nonsym": convdiff2d(7, 5.0).toarray()[:n, :n],
+         "cplx": complex_tridiag(n).toarray()}[family]
+    zero_op = np.zeros((n, n))
+    for op_mat, r0 in ((A, np.zeros(n)), (zero_op, np.ones(n))):
+        res = []
+        for cls in (Oracle, HostDouble):
+            if family == "cplx":
+                r = cls().solve_complex(lambda x: (op_mat @ x).astype(complex), n, 3, 12, "LM", tol=1e-8, mxiter=50,
+                                        resid=r0.astype(complex), eupd=False)
+            else:
+                r = cls().solve(lambda x: op_mat @ x, n, 3, 12, "LM", sym=(family == "sym"), tol=1e-8, mxiter=50,
+                                resid=r0, eupd=False)
+            res.append((r.info, int(r.iparam[2]), int(r.iparam[4]), int(r.iparam[8])))
+        assert res[0][0] == -9 and res[0] == res[1], res
