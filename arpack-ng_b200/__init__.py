@@ -269,7 +269,7 @@ def alloc_device_buffers(n, ncv, dtype=np.float64, device="cuda"):
 
 def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.float64,
           bop=None, rvec=True, sigma=0.0, sigmai=0.0, device="cuda", host_buffers=False, comm=None, ishift=1,
-          eupd=True, pinned=True, registered_op=None, buffers=None):
+          eupd=True, pinned=True, registered_op=None, buffers=None, howmny="A"):
     """Run a whole *aupd/*eupd solve through the C-ABI.
 
     device arrays (default): resid/v/workd are torch CUDA tensors; ``op(x, y)`` receives tensor views of the
@@ -382,14 +382,14 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
     ierr = np.zeros(1, dtype=np.int32)
     if sym:
         d = np.zeros(nev, dtype=np_dt)
-        dseupd_c(rvec, "A", select, d, v, ldv, sigma, bmat, n, which, nev, tol, res, ncv, v, ldv, iparam, ipntr, workd,
+        dseupd_c(rvec, howmny, select, d, v, ldv, sigma, bmat, n, which, nev, tol, res, ncv, v, ldv, iparam, ipntr, workd,
                  workl, ierr, comm=comm)
         out.update(d=d, z=v, ierr=int(ierr[0]))
     else:
         dr = np.zeros(nev + 1, dtype=np_dt)
         di = np.zeros(nev + 1, dtype=np_dt)
         workev = np.zeros(3 * ncv, dtype=np_dt)
-        dneupd_c(rvec, "A", select, dr, di, v, ldv, sigma, sigmai, workev, bmat, n, which, nev, tol, res, ncv, v, ldv,
+        dneupd_c(rvec, howmny, select, dr, di, v, ldv, sigma, sigmai, workev, bmat, n, which, nev, tol, res, ncv, v, ldv,
                  iparam, ipntr, workd, workl, ierr, comm=comm)
         out.update(dr=dr, di=di, z=v, ierr=int(ierr[0]))
     out.update(workl_eupd=workl.copy(), ipntr_eupd=ipntr.copy())
@@ -398,7 +398,8 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
 
 
 def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode=1, resid=None, dtype=np.complex128,
-                  bop=None, rvec=True, sigma=0.0, device="cuda", host_buffers=False, ishift=1, eupd=True, comm=None):
+                  bop=None, rvec=True, sigma=0.0, device="cuda", host_buffers=False, ishift=1, eupd=True, comm=None,
+                  howmny="A"):
     """znaupd_c/zneupd_c (cnaupd_c/cneupd_c for complex64) solve through the C-ABI, the loop of
     EXAMPLES/COMPLEX/zndrv1.f.  Device arrays (default): ``op(x, y)`` gets complex CUDA tensor views of the workd slots;
     host_buffers=True: numpy views.  Mode 3 with bmat='G': ``op(x, y, bx)`` also receives workd(ipntr(3)) at ido = 1."""
@@ -467,7 +468,7 @@ def solve_complex(op, n, nev, ncv, which, *, tol=0.0, mxiter=300, bmat="I", mode
     d = np.zeros(nev + 1, dtype=np_dt)
     workev = np.zeros(2 * ncv, dtype=np_dt)
     sg = complex(sigma)
-    eargs = (int(rvec), b"A", select.ctypes.data_as(c_int_p), _addr(d), _addr(v), ldv, rt(sg.real), rt(sg.imag),
+    eargs = (int(rvec), howmny.encode(), select.ctypes.data_as(c_int_p), _addr(d), _addr(v), ldv, rt(sg.real), rt(sg.imag),
              _addr(workev), bmat.encode(), n, which.encode(), nev, rt(tol), _addr(res), ncv, _addr(v), ldv,
              iparam.ctypes.data_as(c_int_p), ipntr.ctypes.data_as(c_int_p), _addr(workd), _addr(workl), lworkl, rwp,
              ierr.ctypes.data_as(c_int_p))
