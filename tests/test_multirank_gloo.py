@@ -34,6 +34,12 @@ def _rank_main(rank, world, port, q):
         r = cls(rank=rank, nranks=world, allreduce=allreduce).solve(lambda x: diag * x, cnt, 9, 19, "LM", tol=1e-6,
                                                                      mxiter=10000, c_abi_tol=True)
         out[name] = (r.info, r.ierr, r.d.copy(), [int(v) for v in r.iparam], float(np.sum(r.z[:9] ** 2)))
+    # the complex twins pznaupd/pzneupd (PARPACK/TESTS/MPI/icb_parpack_c.c:104-190): diag((i+1)(1+i)), rvec = 0
+    zdiag = np.arange(first + 1, first + cnt + 1) * (1 + 1j)
+    for name, cls in (("product_host_logic_z", HostDouble), ("oracle_z", Oracle)):
+        r = cls(rank=rank, nranks=world, allreduce=allreduce).solve_complex(lambda x: zdiag * x, cnt, 9, 19, "LM", tol=1e-6,
+                                                                            mxiter=10000, rvec=False, c_abi_tol=True)
+        out[name] = (r.info, r.ierr, r.d.copy(), [int(v) for v in r.iparam])
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, out))
@@ -46,7 +52,7 @@ def test_pdsaupd_semantics_world_size_2_gloo():
     port = 29500 + (os.getpid() % 2000)
     procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    res = dict(q.get(timeout=240) for _ in range(2))
+    res = dict(q.get(timeout=400) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     for rank in (0, 1):
         for name in ("product_host_logic", "oracle"):
@@ -56,6 +62,13 @@ def test_pdsaupd_semantics_world_size_2_gloo():
         # host logic == oracle on every rank: counts identical, eigenvalues to rounding
         assert res[rank]["product_host_logic"][3] == res[rank]["oracle"][3]
         assert np.abs(res[rank]["product_host_logic"][2] - res[rank]["oracle"][2]).max() < 1e-9
+        # complex twins: known answer (992+i)(1+i), host logic == oracle
+        want = np.arange(992, 1001) * (1 + 1j)
+        for name in ("product_host_logic_z", "oracle_z"):
+            info, ierr, d, iparam = res[rank][name]
+            assert info == 0 and ierr == 0
+            assert np.abs(d.real - want.real).max() < 1e-5 and np.abs(d.imag - want.imag).max() < 1e-5
+        assert res[rank]["product_host_logic_z"][3] == res[rank]["oracle_z"][3]
     # replicated quantities agree across ranks; local Ritz-vector blocks assemble to 9 unit vectors
     assert res[0]["oracle"][3] == res[1]["oracle"][3]
     assert abs(res[0]["product_host_logic"][4] + res[1]["product_host_logic"][4] - 9.0) < 1e-8
