@@ -515,7 +515,7 @@ void debug_c(a_int logfil, a_int ndigit, a_int mgetv0, a_int msaupd, a_int msaup
   std::memcpy(g_debug.v, vals, sizeof(vals));
   // COMMON /debug/ as the host control code sees it (trace.hpp): same 24 integers, same order (debug.h:8-16)
   static_assert(sizeof(TraceLevels) == sizeof(vals), "TraceLevels mirrors COMMON /debug/");
-  std::memcpy(&trace_levels(), vals, sizeof(vals));
+  std::memcpy(static_cast<void*>(&trace_levels()), vals, sizeof(vals));
 }
 void sstats_c(void) { g_last_counters = Counters(); }
 void sstatn_c(void) { g_last_counters = Counters(); }

@@ -255,7 +255,7 @@ long long hd_speculative_hits(void* p, int is_double, int fam_sym) {
   return fam_sym ? q->sym->speculative_hits() : q->nonsym->speculative_hits();
 }
 // COMMON /debug/ of the control code under test (what debug_c does in the product, api.cu)
-void hd_debug(const int* levels24) { std::memcpy(&trace_levels(), levels24, sizeof(TraceLevels)); }
+void hd_debug(const int* levels24) { std::memcpy(static_cast<void*>(&trace_levels()), levels24, sizeof(TraceLevels)); }
 void hd_stats(void* p, int is_double, int fam_sym, int* out5) {
   const Counters* c = nullptr;
   if (is_double) { auto* q = (Proc<double>*)p; c = fam_sym ? &q->sym->counters() : &q->nonsym->counters(); }

@@ -2,6 +2,7 @@
 //
 // Plain-loop VecOps<std::complex<R>> so that the CPU test-suite can drive the product's complex host control code
 // (arpack-ng_b200/csrc/irl_complex.hpp) without a GPU.  Uses nothing under oracle/.
+#include <algorithm>
 #include <complex>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +56,7 @@ struct HostVecOpsZ final : VecOps<std::complex<R>> {
   void copy(int64_t n, const T* x, T* y) override {
     if (x != y) std::memmove(y, x, sizeof(T) * (size_t)n);
   }
-  void zero(int64_t n, T* x) override { std::memset(x, 0, sizeof(T) * (size_t)n); }
+  void zero(int64_t n, T* x) override { std::fill(x, x + n, T(0)); }
   void scal(int64_t n, T a, T* x) override {
     for (int64_t i = 0; i < n; ++i) x[i] *= a;
   }
