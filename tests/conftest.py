@@ -37,3 +37,25 @@ def _native_built():
     backends.build()
     backends.build_hostdouble()
     yield
+
+
+@pytest.fixture(scope="session")
+def ab_comm():
+    """(package, comm handle) for the PARPACK entry points on the GPU: ONE 1-rank NCCL process group and ONE library
+    communicator for the whole session, shared by every test module that needs them (no re-initialisation of NCCL
+    inside a process)."""
+    import torch
+    import torch.distributed as dist
+    import arpack_ng_b200 as ab
+    ab.lib()
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 1500))
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    comm = ab.nccl_comm_from_torch_distributed()
+    yield ab, comm
+    ab.lib().ab200_comm_destroy(comm)
+    if created:
+        dist.destroy_process_group()

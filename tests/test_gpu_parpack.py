@@ -17,25 +17,6 @@ pytestmark = pytest.mark.gpu
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def ab_comm():
-    import torch
-    import torch.distributed as dist
-    import arpack_ng_b200 as ab
-    ab.lib()
-    created = False
-    if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 1500))
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
-        created = True
-    comm = ab.nccl_comm_from_torch_distributed()
-    yield ab, comm
-    ab.lib().ab200_comm_destroy(comm)
-    if created:
-        dist.destroy_process_group()
-
-
 def _self_allreduce(arr, op):
     return arr
 

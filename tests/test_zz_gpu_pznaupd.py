@@ -6,33 +6,12 @@ PARPACK/TESTS/MPI/icb_parpack_c.c:104-190.
 The CPU side of the same path (oracle and host logic on 2 and 3 logical ranks) is covered by
 tests/test_complex_cpu.py; the kernels are those of the sequential complex path.  Observed passing on a B200 with a
 1-rank communicator; a multi-rank GPU run has not been made yet."""
-import os
-
 import numpy as np
 import pytest
 
 from backends import Oracle
 
 pytestmark = pytest.mark.gpu
-
-
-@pytest.fixture(scope="module")
-def ab_comm():
-    import torch
-    import torch.distributed as dist
-    import arpack_ng_b200 as ab
-    ab.lib()
-    created = False
-    if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", str(29700 + os.getpid() % 1500))
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
-        created = True
-    comm = ab.nccl_comm_from_torch_distributed()
-    yield ab, comm
-    ab.lib().ab200_comm_destroy(comm)
-    if created:
-        dist.destroy_process_group()
 
 
 def _self_allreduce(arr, op):
