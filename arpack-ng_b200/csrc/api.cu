@@ -186,9 +186,9 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
       [d](const T* x, T* y) {
         if (csr_op_apply<T>(d, x, y) != 0) throw CudaError("registered CSR operator: SpMV launch failed");
       },
-      [d, ops](T inv, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
-        const int rc = csr_op_apply_fused<T>(d, inv, resid, vj, y, ops->reduction_scratch(2 * 148 * 16), mb_dots,
-                                             ops->reduction_ticket());
+      [d, ops](T inv, const StepGate<T>* gate, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+        const int rc = csr_op_apply_fused<T>(d, inv, gate, ops->stop_flag(), resid, vj, y,
+                                             ops->reduction_scratch(2 * 148 * 16), mb_dots, ops->reduction_ticket());
         if (rc < 0) throw CudaError("registered CSR operator: fused SpMV launch failed");
         return rc == 0;
       });
@@ -227,6 +227,13 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
         std::lock_guard<std::mutex> lk(g_mu);
         registered_ops<T>().erase(workl);  // not applicable to this solve (bmat='G', modes 2-5)
       }
+      // device-resident sweeps (no host round trip per step) need hand-off slots the device reaches by itself: a
+      // device-resident workd, or a registered operator (then no hand-off happens at all)
+      {
+        const bool has_op = SYM ? c->sym->has_registered_op() : c->nonsym->has_registered_op();
+        if (SYM) c->sym->set_deferral(!c->workd_host || has_op);
+        else c->nonsym->set_deferral(!c->workd_host || has_op);
+      }
       if (*info != 0 && c->resid_host && n > 0) c->ops->upload(c->resid_d, resid, (size_t)n);
     } else {
       c = find_ctx<T>(workl);
@@ -234,7 +241,7 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
       // the user's result of the previous hand-off
       if (c->workd_host && (c->last_ido == -1 || c->last_ido == 1 || c->last_ido == 2)) {
         c->ops->upload(c->workd_d + c->last_ipntr[1] - 1, c->workd_u + c->last_ipntr[1] - 1, (size_t)c->n);
-        if (c->mode == 2 && c->last_ido == 1)  // mode 2: x was overwritten with A*x (dsaupd.f:309-313)
+        if (SYM && c->mode == 2 && c->last_ido == 1)  // dsaupd mode 2: x was overwritten with A*x (dsaupd.f:309-313)
           c->ops->upload(c->workd_d + c->last_ipntr[0] - 1, c->workd_u + c->last_ipntr[0] - 1, (size_t)c->n);
       }
     }

@@ -14,6 +14,7 @@
 
 #include "../../include/arpack_b200.h"
 #include "driver.hpp"
+#include "gate.cuh"
 #include "tma_common.cuh"
 #include "vecops_cuda.cuh"
 
@@ -82,8 +83,16 @@ __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* 
                                                           const T* __restrict__ x, T* __restrict__ y, int nloc,
                                                           const T* __restrict__ xh, T xs, T* __restrict__ vj_out,
                                                           T* __restrict__ partial, T* __restrict__ dots_out,
-                                                          unsigned int* ticket) {
+                                                          unsigned int* ticket, const StepGate<T> gate,
+                                                          const T* stop) {
   __shared__ T prod[CAP];
+  if (FUSED) {
+    if (stopped(stop)) return;
+    if (gate.stop != nullptr && !gate_eval(gate, xs)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
+      return;
+    }
+  }
   __shared__ int srow[ROWS + 1];
   __shared__ T red[2][ROWS / 32];
   const int tid = threadIdx.x;
@@ -179,8 +188,16 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
                                                              const T* __restrict__ x, T* __restrict__ y, int nloc,
                                                              const T* __restrict__ xh, T xs, T* __restrict__ vj_out,
                                                              T* __restrict__ partial, T* __restrict__ dots_out,
-                                                             unsigned int* ticket) {
+                                                             unsigned int* ticket, const StepGate<T> gate,
+                                                             const T* stop) {
   constexpr int CAP = ROWS * EPT;  // entries per ring slot, alignment pad included
+  if (FUSED) {
+    if (stopped(stop)) return;
+    if (gate.stop != nullptr && !gate_eval(gate, xs)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
+      return;
+    }
+  }
   using Stage = SpmvBulkStage<T, ROWS, CAP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
 template <typename T, int ROWS, int EPT, int NST, bool FUSED>
 int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long nnz, const int* rowptr, const int* col,
                          const T* val, const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial,
-                         T* dots_out, unsigned int* ticket) {
+                         T* dots_out, unsigned int* ticket, const StepGate<T>& gate, const T* stop) {
   using Stage = SpmvBulkStage<T, ROWS, ROWS * EPT>;
   constexpr size_t smem = sizeof(Stage) * NST + 2 * NST * sizeof(uint64_t);
   auto kern = k_csr_spmv_bulk<T, ROWS, EPT, NST, FUSED>;
@@ -392,7 +409,8 @@ int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long n
   long long g = (long long)sms * ctas_per_sm;
   if (g > nblk) g = nblk;
   (void)nnz;
-  kern<<<(int)g, ROWS + 32, smem, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out, partial, dots_out, ticket);
+  kern<<<(int)g, ROWS + 32, smem, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out, partial, dots_out, ticket,
+                                       gate, stop);
   launch_stats().kernels++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -405,11 +423,11 @@ inline bool spmv_bulk_ok(const int* rowptr, const int* col, const void* val, lon
 template <typename T, bool FUSED>
 int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr, const int* col, const T* val,
                      const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out,
-                     unsigned int* ticket) {
+                     unsigned int* ticket, const StepGate<T>& gate = StepGate<T>(), const T* stop = nullptr) {
   static const int variant = getenv("AB200_SPMV_BULK") ? atoi(getenv("AB200_SPMV_BULK")) : 0;
 #define AB200_BULK_CFG(ROWS_, EPT_, NST_, CTAS_)                                                                    \
   return launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, xh, xs,  \
-                                                           vj_out, partial, dots_out, ticket)
+                                                           vj_out, partial, dots_out, ticket, gate, stop)
   // entries per thread and ring slot: a 256-row block of a matrix with avg entries per row holds ~256*avg (+3 of
   // alignment pad); 6 covers 5-point stencils, 8 covers 7-point stencils
   const double avg = (double)nnz / (double)(nrows > 0 ? nrows : 1);
@@ -432,7 +450,8 @@ int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr
 
 template <typename T, bool FUSED>
 int launch_spmv_stream(cudaStream_t s, int nrows, const int* rowptr, const int* col, const T* val, const T* x, T* y,
-                       int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out, unsigned int* ticket) {
+                       int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out, unsigned int* ticket,
+                       const StepGate<T>& gate = StepGate<T>(), const T* stop = nullptr) {
   static const int rows_env = getenv("AB200_SPMV_ROWS") ? atoi(getenv("AB200_SPMV_ROWS")) : 256;
   const long long cap = 148LL * 8;
   if (rows_env == 512) {
@@ -440,19 +459,19 @@ int launch_spmv_stream(cudaStream_t s, int nrows, const int* rowptr, const int* 
     long long g = ((long long)nrows + ROWS - 1) / ROWS;
     const int grid = (int)(g > cap / 2 ? cap / 2 : g);
     k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
-                                                               partial, dots_out, ticket);
+                                                               partial, dots_out, ticket, gate, stop);
   } else if (rows_env == 128) {
     constexpr int ROWS = 128, CAP = 9 * 128;
     long long g = ((long long)nrows + ROWS - 1) / ROWS;
     const int grid = (int)(g > cap * 2 ? cap * 2 : g);
     k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
-                                                               partial, dots_out, ticket);
+                                                               partial, dots_out, ticket, gate, stop);
   } else {
     constexpr int ROWS = 256, CAP = 9 * 256;
     long long g = ((long long)nrows + ROWS - 1) / ROWS;
     const int grid = (int)(g > cap ? cap : g);
     k_csr_spmv_stream<T, ROWS, CAP, FUSED><<<grid, ROWS, 0, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out,
-                                                               partial, dots_out, ticket);
+                                                               partial, dots_out, ticket, gate, stop);
   }
   launch_stats().kernels++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -674,8 +693,8 @@ int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y) {
   return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, 0, nullptr, op.nnz);
 }
 template <typename T>
-int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* y, T* partial, T* dots_out,
-                       unsigned int* ticket) {
+int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const StepGate<T>* gate, const T* stop, const T* resid, T* vj,
+                       T* y, T* partial, T* dots_out, unsigned int* ticket) {
   if (op.nrows <= 0) return 0;
   const double avg = op.nnz > 0 ? (double)op.nnz / op.nrows : 8.0;
   if (avg > 7.9) return 1;  // caller falls back to start_step + plain SpMV
@@ -691,18 +710,19 @@ int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* 
     if (exchange_halo(op, resid) != 0) return -1;
     dots_out = nullptr;
   }
+  const StepGate<T> g = gate ? *gate : StepGate<T>();
   if (spmv_bulk_ok(op.rowptr, op.col, op.val, op.nnz))
     return launch_spmv_bulk<T, true>(s, op.nrows, op.nnz, op.rowptr, op.col, op.val, resid, y, nloc, xh, inv, vj,
-                                     partial, dots_out, ticket);
+                                     partial, dots_out, ticket, g, stop);
   return launch_spmv_stream<T, true>(s, op.nrows, op.rowptr, op.col, op.val, resid, y, nloc, xh, inv, vj, partial,
-                                     dots_out, ticket);
+                                     dots_out, ticket, g, stop);
 }
 template int csr_op_apply<double>(const CsrOpDesc<double>&, const double*, double*);
 template int csr_op_apply<float>(const CsrOpDesc<float>&, const float*, float*);
-template int csr_op_apply_fused<double>(const CsrOpDesc<double>&, double, const double*, double*, double*, double*,
-                                        double*, unsigned int*);
-template int csr_op_apply_fused<float>(const CsrOpDesc<float>&, float, const float*, float*, float*, float*, float*,
-                                       unsigned int*);
+template int csr_op_apply_fused<double>(const CsrOpDesc<double>&, double, const StepGate<double>*, const double*,
+                                        const double*, double*, double*, double*, double*, unsigned int*);
+template int csr_op_apply_fused<float>(const CsrOpDesc<float>&, float, const StepGate<float>*, const float*,
+                                       const float*, float*, float*, float*, float*, unsigned int*);
 }  // namespace ab200
 
 using namespace ab200;

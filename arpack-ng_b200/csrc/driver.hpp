@@ -1,5 +1,6 @@
 // driver.hpp -- C++ view of the driver-layer operators for the solver's registered-operator mode.
 #pragma once
+#include "vecops.hpp"
 namespace ab200 {
 
 // A square CSR operator resident in HBM (int32 indices), registered for a solve with ab200_register_csr_op_*.
@@ -22,8 +23,10 @@ template <typename T>
 int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y);
 // Fused K1+K2+K3: v_j = inv*resid, y = A v_j, dots_out = {v_j^T y, y^T y}; returns 1 when the operator's row
 // lengths do not suit the fused kernel (the caller then runs start_step + csr_op_apply)
+// gate != nullptr: the scale is formed on the device from the previous step's mailbox slot (device-resident sweep),
+// and the kernel exits at once when the sweep's stop flag is set or the gate trips (see StepGate, vecops.hpp)
 template <typename T>
-int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const T* resid, T* vj, T* y, T* partial, T* dots_out,
-                       unsigned int* ticket);
+int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const StepGate<T>* gate, const T* stop, const T* resid, T* vj,
+                       T* y, T* partial, T* dots_out, unsigned int* ticket);
 
 }  // namespace ab200

@@ -10,7 +10,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <stdexcept>
 #include <vector>
 
 #include "hostmath.hpp"
@@ -68,9 +71,15 @@ class IrlBase {
   const Counters& counters() const { return cnt; }
   // largest relative disagreement between the SpMV-epilogue dots and the CGS sweep (registered-operator mode)
   T fused_dot_maxdiff = 0;
-  long long speculative_hits() const { return cnt_spec_hits_; }  // steps whose K1+K2 ran ahead of the host fetch
-  void set_registered_op(std::function<void(const T*, T*)> op,
-                         std::function<bool(T, const T*, T*, T*, T*)> fused) {
+  // steps that ran inside a device-resident batch (no host round trip), and batches cut short by a rare path
+  long long deferred_steps() const { return cnt_deferred_steps_; }
+  long long deferred_trips() const { return cnt_deferred_trips_; }
+  long long host_round_trips() const { return cnt_round_trips_; }
+  // deferral needs hand-off slots the device can reach without the host (device-resident workd or a registered OP)
+  void set_deferral(bool on) { defer_enabled_ = on; }
+  bool has_registered_op() const { return (bool)op_; }
+  using FusedOp = std::function<bool(T inv, const StepGate<T>* gate, const T* resid, T* vj, T* y, T* mb_dots)>;
+  void set_registered_op(std::function<void(const T*, T*)> op, FusedOp fused) {
     op_ = std::move(op);
     fused_op_ = std::move(fused);
   }
@@ -100,10 +109,15 @@ class IrlBase {
   int ido_ = 0;
   int ipntr_[3] = {0, 0, 0};
 
-  // mailbox layout: three segments of seg_ entries each
+  // mailbox layout: slot 0 = three segments of seg_ entries each (the synchronous paths), then 4 entries for the
+  // sticky stop flag of a device-resident batch, then one 3*seg_ slot per step of such a batch (at most ncv)
   T* mb_ = nullptr;
   int seg_ = 0;
-  std::vector<T> mbh_;  // host copy
+  std::vector<T> mbh_;  // host copy of slot 0
+  std::vector<T> logh_; // host copy of [stop | batch slots]
+  T* mb_stop() { return mb_ + (size_t)3 * seg_; }
+  T* slot_dev(int s) { return mb_ + (size_t)3 * seg_ + 4 + (size_t)3 * seg_ * (s - 1); }   // s = 1..ncv
+  const T* slot_host(int s) const { return logh_.data() + 4 + (size_t)3 * seg_ * (s - 1); }
   T* mbA() { return mb_; }
   T* mbB() { return mb_ + seg_; }
   T* mbC() { return mb_ + 2 * seg_; }
@@ -116,20 +130,23 @@ class IrlBase {
   // registered operator (opt-in extension, mode 1 / bmat='I'): the solver applies OP itself instead of
   // returning ido = +-1, so a whole solve is one *aupd call (the arpackmm-style driver loop, natively)
   std::function<void(const T* x, T* y)> op_;
-  std::function<bool(T inv, const T* resid, T* vj, T* y, T* mb_dots)> fused_op_;
+  FusedOp fused_op_;
   bool ai_fused_op_ = false;
-  bool ai_spec_hit_ = false;
-  bool spec_issued_ = false;   // a speculative K1+K2 for the next step is in the stream
-  T spec_rnorm_ = 0;           // the norm it scaled with
-  long long cnt_spec_hits_ = 0;
+  // device-resident batch state
+  bool defer_enabled_ = false;
+  int df_first_ = 0, df_last_ = 0, df_j_ = 0;
+  std::vector<char> df_fused_;
+  long long cnt_deferred_steps_ = 0, cnt_deferred_trips_ = 0, cnt_round_trips_ = 0;
 
   T* vcol(int j1) { return v_ + (int64_t)(j1 - 1) * ldv_; }  // 1-based column
   T* slot(int off1) { return workd_ + (off1 - 1); }           // 1-based workd offset
 
   void setup_mailbox() {
     seg_ = ncv_ + 2;
-    mb_ = ops_->mailbox((size_t)3 * seg_);
+    mb_ = ops_->mailbox((size_t)3 * seg_ * (ncv_ + 1) + 4);
     mbh_.assign((size_t)3 * seg_, T(0));
+    logh_.assign((size_t)3 * seg_ * ncv_ + 4, T(0));
+    df_fused_.assign((size_t)ncv_ + 2, 0);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -235,6 +252,10 @@ class IrlBase {
   virtual void h_add(int j, const T* scol, bool after_restart) = 0;            // DGKS correction
   virtual void sweep_done(int k, int np) = 0;
   virtual T tiny_norm() = 0;  // dsaitr: safmin; dnaitr: unfl after dlabad
+  // dsaitr's mode-2 contract (dsaupd.f:309-313, dsaitr.f:504-515): the caller overwrote x with A*x, so B*OP*x is
+  // taken from workd(ivj) and the ido = 2 hand-off is skipped.  dnaitr.f has no such shortcut (it has no mode
+  // argument at all): the nonsymmetric solver always issues ido = 2 for bmat = 'G'.
+  virtual bool mode2_shortcut() const { return false; }
 
   int ai_pc_ = 0, ai_k_ = 0, ai_np_ = 0, ai_j_ = 0, ai_itry_ = 0, ai_iter_ = 0, ai_info_ = 0;
   bool ai_rstart_ = false;
@@ -244,12 +265,59 @@ class IrlBase {
   int irj() const { return 1 + n_; }
   int ivj() const { return 1 + 2 * n_; }
 
-  // generic B-norm of resid: bmat='G' needs a hand-off, so only the tail is here
+  bool can_defer() {
+    static const bool off = getenv("AB200_DEFER") && std::strcmp(getenv("AB200_DEFER"), "0") == 0;
+    return !off && defer_enabled_ && ops_->deferred_ok() && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm() &&
+           rnorm_ > T(0);
+  }
+
+  // Host side of one orthogonalisation whose reductions are in hA()/hB()/hC() (dsaitr.f:552-780 for bmat = 'I'):
+  // H column, DGKS bookkeeping and -- rare -- the third pass, which runs synchronously on the device.
+  void finish_orth() {
+    if (ai_fused_op_ && !par_) {
+      // alpha = v_j^T OP v_j and ||OP v_j||^2 from the SpMV epilogue must agree with the CGS sweep
+      const T da = std::fabs(hC()[2] - hA()[ai_j_ - 1]), dw = std::fabs(hC()[3] - hA()[ai_j_]);
+      const T sc = std::sqrt(hA()[ai_j_]);
+      fused_dot_maxdiff = std::max(fused_dot_maxdiff, std::max(da / (sc > T(0) ? sc : T(1)),
+                                                               dw / (hA()[ai_j_] > T(0) ? hA()[ai_j_] : T(1))));
+    }
+    ai_wnorm_ = std::sqrt(hA()[ai_j_]);
+    h_store(ai_j_, hA(), ai_beta_, ai_rstart_);
+    rnorm_ = std::sqrt(hB()[ai_j_]);
+    if (!(rnorm_ > dgks_threshold<T>() * ai_wnorm_)) {
+      cnt.nrorth++;
+      h_add(ai_j_, hB(), ai_rstart_);
+      ai_rnorm1_ = std::sqrt(hC()[0]);
+      if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
+        rnorm_ = ai_rnorm1_;
+      } else {
+        // one more refinement pass (iter = 1), then give up (dsaitr.f:768-780)
+        cnt.nitref++;
+        rnorm_ = ai_rnorm1_;
+        ops_->dots(n_, ai_j_, v_, ldv_, resid_, resid_, mbA());
+        ops_->allreduce_sum(mbA(), (size_t)ai_j_);
+        ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, mbC());
+        ops_->allreduce_sum(mbC(), 1);
+        ops_->fetch(hA(), mbA(), (size_t)ai_j_);
+        ops_->fetch(hC(), mbC(), 1);
+        cnt_round_trips_ += 2;
+        h_add(ai_j_, hA(), ai_rstart_);
+        ai_rnorm1_ = std::sqrt(std::fabs(hC()[0]));
+        if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
+          rnorm_ = ai_rnorm1_;
+        } else {
+          cnt.nitref++;
+          ops_->zero(n_, resid_);
+          rnorm_ = 0;
+        }
+      }
+    }
+  }
+
   // returns true when finished; ai_info_ > 0 <=> no restart vector could be found (info = j-1)
   bool extend() {
     CO_BEGIN(ai_pc_)
     ai_info_ = 0;
-    spec_issued_ = false;
     for (ai_j_ = ai_k_ + 1; ai_j_ <= ai_k_ + ai_np_; ++ai_j_) {
       ai_beta_ = rnorm_;
       ai_rstart_ = false;
@@ -272,20 +340,78 @@ class IrlBase {
           return true;
         }
       }
+      if (can_defer()) {
+        // ---- device-resident batch (bmat = 'I', mode 1): steps ai_j_ .. k+np are enqueued back to back, the
+        // host reads ONE block of mailbox slots when the batch is over and replays its bookkeeping from it ----
+        df_first_ = ai_j_;
+        df_last_ = ai_k_ + ai_np_;
+        ops_->zero(4, mb_stop());
+        ops_->set_stop_flag(mb_stop());
+        for (df_j_ = df_first_; df_j_ <= df_last_; ++df_j_) {
+          {
+            const int s = df_j_ - df_first_ + 1;
+            T* sC = slot_dev(s) + 2 * seg_;
+            StepGate<T> g;
+            const bool first = (df_j_ == df_first_);
+            if (!first) {
+              g.A = slot_dev(s - 1); g.B = slot_dev(s - 1) + seg_; g.C = slot_dev(s - 1) + 2 * seg_;
+              g.prev_j = df_j_ - 1; g.tiny = tiny_norm(); g.stop = mb_stop(); g.stop_code = T(df_j_ - 1);
+            }
+            // v_j = r/||r||, x = v_j (dsaitr.f:438-468); with a registered operator K1+K2+K3 are one kernel
+            bool fused = false;
+            if (fused_op_) fused = fused_op_(first ? T(1) / rnorm_ : T(0), first ? nullptr : &g, resid_, vcol(df_j_),
+                                             slot(irj()), sC + 2);
+            if (!fused) {
+              if (first) ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(df_j_), slot(ivj()), nullptr, true);
+              else ops_->start_step_gated(n_, g, resid_, vcol(df_j_), slot(ivj()), nullptr);
+            }
+            df_fused_[s] = fused ? 1 : 0;
+            if (op_ && !fused) op_(slot(ivj()), slot(irj()));
+          }
+          if (!op_) {
+            ipntr_[0] = ivj(); ipntr_[1] = irj(); ipntr_[2] = IPJ;
+            ido_ = 1;
+            CO_YIELD(ai_pc_);
+          }
+          {
+            T* sA = slot_dev(df_j_ - df_first_ + 1);
+            ops_->orth_step(n_, df_j_, v_, ldv_, slot(irj()), resid_, sA, sA + seg_, sA + 2 * seg_);
+          }
+        }
+        ops_->set_stop_flag(nullptr);
+        ops_->fetch(logh_.data(), mb_stop(), (size_t)4 + (size_t)3 * seg_ * (df_last_ - df_first_ + 1));
+        cnt_round_trips_++;
+        // replay: the host logic of every step, in order, from the step's own mailbox slot
+        for (; ai_j_ <= df_last_; ++ai_j_) {
+          if (ai_j_ > df_first_) { ai_beta_ = rnorm_; ai_rstart_ = false; }
+          std::copy(slot_host(ai_j_ - df_first_ + 1), slot_host(ai_j_ - df_first_ + 1) + 3 * seg_, mbh_.begin());
+          ai_fused_op_ = df_fused_[ai_j_ - df_first_ + 1] != 0;
+          cnt.nopx++;
+          cnt_deferred_steps_++;
+          {
+            const int nitref0 = cnt.nitref;
+            finish_orth();
+            const bool rare = cnt.nitref != nitref0 || !(rnorm_ >= tiny_norm()) || !(rnorm_ > T(0));
+            if (ai_j_ < df_last_) {
+              // the device took the same decision in the gated start of step j+1: later kernels were early exits
+              const bool stopped = (logh_[0] == T(ai_j_));
+              if (rare != stopped)
+                throw std::runtime_error("device-resident sweep: host and device disagree on a rare-path decision");
+              if (rare) break;
+            }
+          }
+        }
+        if (ai_j_ <= df_last_) cnt_deferred_trips_++;
+        // a cut-short batch leaves the loop variable on the step it stopped at: the sweep goes on from the next one
+        continue;
+      }
       // v_j = r/||r||, p_j = B r/||r||, x = v_j   (dsaitr.f:438-468)
       ai_fused_op_ = false;
-      // K1+K2 of this step may already have been issued speculatively behind the previous step's kernels (see below):
-      // valid when the host arrived at exactly the norm the device used and took no restart / rescaling path
-      ai_spec_hit_ = spec_issued_ && !ai_rstart_ && rnorm_ == spec_rnorm_ && rnorm_ >= tiny_norm();
-      spec_issued_ = false;
-      if (ai_spec_hit_) {
-        cnt_spec_hits_++;
-      } else
       if (fused_op_ && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm()) {
         // registered operator: K1+K2+K3 in one kernel (v_j written on the way, x never materialised)
-        ai_fused_op_ = fused_op_(T(1) / rnorm_, resid_, vcol(ai_j_), slot(irj()), mbC() + 2);
+        ai_fused_op_ = fused_op_(T(1) / rnorm_, nullptr, resid_, vcol(ai_j_), slot(irj()), mbC() + 2);
       }
-      if (!ai_fused_op_ && !ai_spec_hit_) {
+      if (!ai_fused_op_) {
         const T tiny = tiny_norm();
         if (rnorm_ >= tiny) {
           // mode 1 / bmat 'I': the B*x slot is neither read by this code nor part of the hand-off (ipntr(3) is
@@ -311,61 +437,16 @@ class IrlBase {
         CO_YIELD(ai_pc_);
       }
       // workd(irj) = OP*v_j
-      if (bmat_ == 'I' && mode_ != 2) {
-        // ---- fused path: CGS + speculative DGKS, one host round trip (K4..K10) ----
+      if (bmat_ == 'I' && !mode2_shortcut()) {
+        // ---- fused path: CGS + speculative DGKS dots, one host round trip per step (K4..K10) ----
         ops_->orth_step(n_, ai_j_, v_, ldv_, slot(irj()), resid_, mbA(), mbB(), mbC());
-        if (ai_j_ < ai_k_ + ai_np_ && !fused_op_) {
-          // not the last step of the sweep: issue the next step's v_{j+1} = r/||r|| now, with the norm taken from
-          // the device mailbox, so that the device is busy while the host reads the mailbox and decides
-          ops_->mark_fetch_point();
-          spec_issued_ = ops_->start_step_speculative(n_, ai_j_, mbB(), mbC(), tiny_norm(), resid_, vcol(ai_j_ + 1),
-                                                      slot(ivj()), (bmat_ == 'I' && mode_ == 1) ? nullptr : slot(IPJ));
-          ops_->fetch_marked(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
-          if (spec_issued_) spec_rnorm_ = std::sqrt((hC()[1] != T(0)) ? hC()[0] : hB()[ai_j_]);
-        } else {
-          ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
-        }
-        if (ai_fused_op_ && !par_) {
-          // alpha = v_j^T OP v_j and ||OP v_j||^2 from the SpMV epilogue must agree with the CGS sweep
-          const T da = std::fabs(hC()[2] - hA()[ai_j_ - 1]), dw = std::fabs(hC()[3] - hA()[ai_j_]);
-          const T sc = std::sqrt(hA()[ai_j_]);
-          fused_dot_maxdiff = std::max(fused_dot_maxdiff, std::max(da / (sc > T(0) ? sc : T(1)),
-                                                                   dw / (hA()[ai_j_] > T(0) ? hA()[ai_j_] : T(1))));
-        }
-        ai_wnorm_ = std::sqrt(hA()[ai_j_]);
-        h_store(ai_j_, hA(), ai_beta_, ai_rstart_);
-        rnorm_ = std::sqrt(hB()[ai_j_]);
-        if (!(rnorm_ > dgks_threshold<T>() * ai_wnorm_)) {
-          cnt.nrorth++;
-          h_add(ai_j_, hB(), ai_rstart_);
-          ai_rnorm1_ = std::sqrt(hC()[0]);
-          if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
-            rnorm_ = ai_rnorm1_;
-          } else {
-            // one more refinement pass (iter = 1), then give up (dsaitr.f:768-780)
-            cnt.nitref++;
-            rnorm_ = ai_rnorm1_;
-            ops_->dots(n_, ai_j_, v_, ldv_, resid_, resid_, mbA());
-            ops_->allreduce_sum(mbA(), (size_t)ai_j_);
-            ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, mbC());
-            ops_->allreduce_sum(mbC(), 1);
-            ops_->fetch(hA(), mbA(), (size_t)ai_j_);
-            ops_->fetch(hC(), mbC(), 1);
-            h_add(ai_j_, hA(), ai_rstart_);
-            ai_rnorm1_ = std::sqrt(std::fabs(hC()[0]));
-            if (ai_rnorm1_ > dgks_threshold<T>() * rnorm_) {
-              rnorm_ = ai_rnorm1_;
-            } else {
-              cnt.nitref++;
-              ops_->zero(n_, resid_);
-              rnorm_ = 0;
-            }
-          }
-        }
+        ops_->fetch(mbh_.data(), mb_, (size_t)2 * seg_ + 4);
+        cnt_round_trips_++;
+        finish_orth();
       } else {
         // ---- generic path (bmat='G' and/or mode 2): B-inner products need hand-offs ----
         ops_->copy(n_, slot(irj()), resid_);
-        if (mode_ != 2) {
+        if (!mode2_shortcut()) {
           // bmat == 'G' here
           cnt.nbx++;
           ipntr_[0] = irj(); ipntr_[1] = IPJ;
@@ -373,7 +454,7 @@ class IrlBase {
           CO_YIELD(ai_pc_);
         }
         // wnorm and the CGS coefficients use B*OP*v_j: workd(ipj), or workd(ivj) = A*v_j in mode 2
-        ops_->dots(n_, ai_j_, v_, ldv_, mode_ == 2 ? slot(ivj()) : slot(IPJ), resid_, mbA());
+        ops_->dots(n_, ai_j_, v_, ldv_, mode2_shortcut() ? slot(ivj()) : slot(IPJ), resid_, mbA());
         ops_->allreduce_sum(mbA(), (size_t)ai_j_ + 1);
         ops_->update(n_, ai_j_, v_, ldv_, mbA(), resid_, resid_, bmat_ == 'I' ? mbC() : nullptr);
         ops_->fetch(hA(), mbA(), (size_t)ai_j_ + 1);

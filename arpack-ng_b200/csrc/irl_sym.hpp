@@ -248,7 +248,10 @@ class IrlSym : public IrlBase<T> {
       for (int k = 0; k < nconv; ++k)
         W[iw + k] = (par_ ? W[iq + k * ldq + ncv - 1] : W[iw + ncv + k]) / (W[iw + k] - T(1));
     }
-    if ((par_ || rvec) && type != REGULR) ops_->ger(n, nconv, resid_dev, W + iw, z_dev, ldz);
+    // pdseupd.f:858 applies this rank-1 update unconditionally -- with rvec = 0 it scribbles uninitialised
+    // coefficients over a Z the caller never asked for.  Deliberate deviation: without rvec nothing is written
+    // (z is not even mapped then), exactly as the sequential dseupd.f:840-857 behaves.
+    if (rvec && z_dev != nullptr && type != REGULR) ops_->ger(n, nconv, resid_dev, W + iw, z_dev, ldz);
   }
 
  private:
@@ -282,6 +285,7 @@ class IrlSym : public IrlBase<T> {
   void sweep_done(int, int) override {}
   int aitr_trace_level() const override { return trace_levels().msaitr; }
   T tiny_norm() override { return safmin_; }
+  bool mode2_shortcut() const override { return mode_ == 2; }
 
   // Ritz values of the kplusp x kplusp tridiagonal and their error bounds rnorm*|last row|
   int ritz_bounds() {

@@ -15,6 +15,23 @@
 
 namespace ab200 {
 
+// How a gated step kernel decides, on the device, whether and with which scale to run: the mailbox segments of
+// the step that precedes it (prev_j columns) hold ||w||^2 = A[prev_j], ||r||^2 = B[prev_j], ||r'||^2 = C[0] and
+// the DGKS flag C[1].  The kernel reproduces the host logic of IrlBase::finish_orth bit for bit:
+//   rn = sqrt(B[j]);  if the DGKS pass ran: rn1 = sqrt(C[0]); rn1 > 0.717*rn ? rn = rn1 : TRIP (third pass)
+//   rn < tiny or rn == 0 -> TRIP (restart / dlascl path);  otherwise scale = 1/rn.
+// On a trip *stop = stop_code and nothing is written.
+template <typename T>
+struct StepGate {
+  const T* A = nullptr;
+  const T* B = nullptr;
+  const T* C = nullptr;
+  int prev_j = 0;
+  T tiny = 0;
+  T* stop = nullptr;
+  T stop_code = 0;
+};
+
 template <typename T>
 struct VecOps {
   virtual ~VecOps() {}
@@ -59,18 +76,19 @@ struct VecOps {
   // (for bmat='I' pass bx_from_resid=true to write bx = resid*inv instead of scaling in place)
   virtual void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx,
                           bool bx_from_resid) = 0;
-  // Speculative K1+K2 of the NEXT step, enqueued before the host has read the mailbox of the orth_step just issued:
-  // the scale is formed on the device, inv = 1/sqrt(mbC[1] != 0 ? mbC[0] : mbB[j]) -- the value the host will derive
-  // in the common path -- and nothing is written when that norm is below `tiny`.  Lets the device work through the
-  // host round trip of fetch_marked().  Returns false when the backend does not support it.
-  virtual bool start_step_speculative(int64_t /*n*/, int /*j*/, const T* /*mbB*/, const T* /*mbC*/, T /*tiny*/,
-                                      const T* /*resid*/, T* /*vj*/, T* /*out_x*/, T* /*bx*/) {
-    return false;
-  }
-  // mark_fetch_point(): remember the current end of the stream; fetch_marked(): like fetch(), but waits only for
-  // the work enqueued before the mark (so kernels issued after it keep running during the copy)
-  virtual void mark_fetch_point() {}
-  virtual void fetch_marked(T* host_dst, const T* mb, size_t count) { fetch(host_dst, mb, count); }
+  // ---- device-resident sweep (IrlBase::extend, deferred mode) ---------------------------------
+  // A whole sweep of Lanczos/Arnoldi steps is enqueued without a host round trip: every step deposits its
+  // reductions in its own mailbox slot, the scale 1/||r|| of the next step and the reference's rare-path tests
+  // (third DGKS pass dsaitr.f:768-780, tiny / zero norm dsaitr.f:378-453) are evaluated on the device by the
+  // gated start of step, and a sticky stop flag turns every later kernel of the sweep into an early exit, so
+  // that the host can resume from exactly the state the reference would be in.
+  virtual bool deferred_ok() const { return false; }
+  // every step kernel (start_step, start_step_gated, orth_step, and a registered operator's fused product)
+  // issued from now on exits at once when *stop != 0; nullptr switches the check off
+  virtual void set_stop_flag(T* /*stop*/) {}
+  // K1+K2 with the scale formed on the device from the previous step's mailbox slot (see StepGate)
+  virtual void start_step_gated(int64_t /*n*/, const StepGate<T>& /*g*/, const T* /*resid*/, T* /*vj*/, T* /*out_x*/,
+                                T* /*bx*/) {}
   // rank-1 purification Z(:,0:k) += resid * w^T  (dseupd.f:857); w is a host vector
   virtual void ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) = 0;
 

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "gate.cuh"
 #include "vecops_cuda.cuh"
 
 namespace ab200 {
@@ -119,8 +120,9 @@ template <typename T, int CC>
 __global__ void __launch_bounds__(kThreads) k_dots(int64_t n, int j, const T* __restrict__ v, int64_t ldv,
                                                    const T* __restrict__ x, const T* __restrict__ y,
                                                    T* __restrict__ partial, int pcols, T* __restrict__ out,
-                                                   unsigned int* ticket) {
+                                                   unsigned int* ticket, const T* stop) {
   __shared__ T red[kWarps][CC + 1];
+  if (stopped(stop)) return;
   const int64_t rpc = ((n + gridDim.x - 1) / gridDim.x + kThreads - 1) / kThreads * kThreads;
   const int64_t r0 = (int64_t)blockIdx.x * rpc;
   const int64_t r1 = (r0 + rpc < n) ? r0 + rpc : n;
@@ -181,10 +183,11 @@ __global__ void __launch_bounds__(kThreads) k_update(int64_t n, int j, const T* 
                                                      const T* __restrict__ coef, const T* src, T* dst,
                                                      T* __restrict__ partial, T* __restrict__ nrm2_out,
                                                      unsigned int* ticket, const T* pred_w2,
-                                                     const T* pred_r2, T* flag_out) {
+                                                     const T* pred_r2, T* flag_out, const T* stop) {
   extern __shared__ unsigned char smem_raw[];
   T* cs = reinterpret_cast<T*>(smem_raw);
   __shared__ T red[kWarps];
+  if (stopped(stop)) return;
   if (pred_w2 != nullptr) {
     const T wn = sqrt(*pred_w2), rn = sqrt(*pred_r2);
     const bool needed = !(rn > T(0.717f) * wn);
@@ -289,7 +292,8 @@ __global__ void k_scal(int64_t n, T alpha, T* x) {
 // K1+K2: v_j = resid*inv, x = v_j, Bx scaled (dsaitr.f:438-442,464)
 template <typename T>
 __global__ void k_start_step(int64_t n, T inv, const T* __restrict__ resid, T* __restrict__ vj,
-                             T* __restrict__ outx, T* bx, bool bx_from_resid) {
+                             T* __restrict__ outx, T* bx, bool bx_from_resid, const T* stop) {
+  if (stopped(stop)) return;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     const T t = resid[r] * inv;
     vj[r] = t;
@@ -298,15 +302,19 @@ __global__ void k_start_step(int64_t n, T inv, const T* __restrict__ resid, T* _
   }
 }
 
-// speculative K1+K2: the scale comes from the mailbox of the orthogonalisation that precedes it on the stream
+// gated K1+K2 of a device-resident sweep: scale and rare-path tests from the previous step's mailbox slot
 template <typename T>
-__global__ void k_start_step_spec(int64_t n, const T* __restrict__ nrm2_plain, const T* __restrict__ nrm2_reorth,
-                                  const T* __restrict__ flag, T tiny, const T* __restrict__ resid, T* __restrict__ vj,
-                                  T* __restrict__ outx, T* bx) {
-  const T val = (*flag != T(0)) ? *nrm2_reorth : *nrm2_plain;
-  const T rn = sqrt(val);
-  if (!(rn >= tiny) || !(rn > T(0))) return;  // the host takes the restart / rescaling path and redoes this step
-  const T inv = T(1) / rn;
+__global__ void k_start_step_gated(int64_t n, const StepGate<T> g, const T* __restrict__ resid, T* __restrict__ vj,
+                                   T* __restrict__ outx, T* bx) {
+  if (stopped(g.stop)) return;
+  T inv;
+  if (!gate_eval(g, inv)) {
+    // every block takes the same decision from the same values; one thread records it.  No block of THIS kernel can
+    // observe the store before its own entry check only if none is scheduled later -- which is why the check above
+    // treats "already stopped" and "stops now" alike: nothing is written either way.
+    if (blockIdx.x == 0 && threadIdx.x == 0) *g.stop = g.stop_code;
+    return;
+  }
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     const T t = resid[r] * inv;
     vj[r] = t;
@@ -462,15 +470,12 @@ CudaVecOps<T>::CudaVecOps(cudaStream_t stream, NcclComm* comm) : stream_(stream)
 
 template <typename T>
 CudaVecOps<T>::~CudaVecOps() {
-  tma_release();
   cudaFree(mb_dev_);
   cudaFreeHost(mb_pinned_);
   cudaFree(partial_);
   cudaFree(ticket_);
   cudaFree(qbuf_);
   cudaFreeHost(qpinned_);
-  if (mark_event_) cudaEventDestroy(mark_event_);
-  if (copy_stream_) cudaStreamDestroy(copy_stream_);
 }
 
 template <typename T>
@@ -528,7 +533,7 @@ T* CudaVecOps<T>::mailbox(size_t count) {
   AB200_CUDA_CHECK(cudaMemsetAsync(mb_dev_, 0, sizeof(T) * mb_count_, stream_));
   // size the reduction scratch once for the whole solve (largest grid x one mailbox segment), so that
   // no step ever pays a synchronising cudaFree/cudaMalloc
-  ensure_partial((size_t)num_sms_ * 8 * (count / 3 + 2));
+  ensure_partial((size_t)num_sms_ * 8 * 72);
   return mb_dev_;
 }
 template <typename T>
@@ -665,41 +670,15 @@ template <typename T>
 void CudaVecOps<T>::start_step(int64_t n, T inv, const T* resid, T* vj, T* outx, T* bx, bool from_resid) {
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? (from_resid ? 4.0 : 5.0) : 3.0));
-  k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid);
+  k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid, stop_);
   AB200_LAUNCHED();
 }
 template <typename T>
-bool CudaVecOps<T>::start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj,
-                                           T* outx, T* bx) {
-  static const bool off = getenv("AB200_SPECULATE") && std::strcmp(getenv("AB200_SPECULATE"), "0") == 0;
-  if (off) return false;
+void CudaVecOps<T>::start_step_gated(int64_t n, const StepGate<T>& g, const T* resid, T* vj, T* outx, T* bx) {
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? 4.0 : 3.0));
-  k_start_step_spec<T><<<grid, 256, 0, stream_>>>(n, mbB + j, mbC, mbC + 1, tiny, resid, vj, outx, bx);
+  k_start_step_gated<T><<<grid, 256, 0, stream_>>>(n, g, resid, vj, outx, bx);
   AB200_LAUNCHED();
-  return true;
-}
-template <typename T>
-void CudaVecOps<T>::mark_fetch_point() {
-  if (!copy_stream_) {
-    AB200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    AB200_CUDA_CHECK(cudaEventCreateWithFlags(&mark_event_, cudaEventDisableTiming));
-  }
-  AB200_CUDA_CHECK(cudaEventRecord(mark_event_, stream_));
-  marked_ = true;
-}
-template <typename T>
-void CudaVecOps<T>::fetch_marked(T* host_dst, const T* mb, size_t count) {
-  if (!marked_) {
-    fetch(host_dst, mb, count);
-    return;
-  }
-  marked_ = false;
-  const size_t off = (size_t)(mb - mb_dev_);
-  AB200_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, mark_event_, 0));
-  AB200_CUDA_CHECK(cudaMemcpyAsync(mb_pinned_ + off, mb, sizeof(T) * count, cudaMemcpyDeviceToHost, copy_stream_));
-  AB200_CUDA_CHECK(cudaStreamSynchronize(copy_stream_));
-  std::memcpy(host_dst, mb_pinned_ + off, sizeof(T) * count);
 }
 template <typename T>
 void CudaVecOps<T>::ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) {
@@ -723,7 +702,7 @@ void CudaVecOps<T>::dots_generic(int64_t n, int j, const T* v, int64_t ldv, cons
   const int pcols = j + 1;
   ensure_partial((size_t)grid * pcols);
   ProfScope ps(stream_, "dots_generic", (double)sizeof(T) * n * (j + (x == y ? 1.0 : 2.0)));
-  k_dots<T, CC><<<grid, kThreads, 0, stream_>>>(n, j, v, ldv, x, y, partial_, pcols, out, ticket_);
+  k_dots<T, CC><<<grid, kThreads, 0, stream_>>>(n, j, v, ldv, x, y, partial_, pcols, out, ticket_, stop_);
   AB200_LAUNCHED();
   launch_stats().fallback++;
 }
@@ -735,7 +714,7 @@ void CudaVecOps<T>::update_generic(int64_t n, int j, const T* v, int64_t ldv, co
   ProfScope ps(stream_, pw2 ? "reorth_generic" : "update_generic", (double)sizeof(T) * n * (j + 2.0));
   k_update<T><<<grid, kThreads, sizeof(T) * (size_t)std::max(j, 1), stream_>>>(n, j, v, ldv, coef, src, dst,
                                                                                partial_, nrm2, ticket_, pw2, pr2,
-                                                                               flag);
+                                                                               flag, stop_);
   AB200_LAUNCHED();
   launch_stats().fallback++;
 }

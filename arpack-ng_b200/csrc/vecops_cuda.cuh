@@ -106,10 +106,9 @@ class CudaVecOps final : public VecOps<T> {
   void dot(int64_t n, const T* x, const T* y, T* mb_out) override;
   void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
   void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx, bool bx_from_resid) override;
-  bool start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj, T* out_x,
-                              T* bx) override;
-  void mark_fetch_point() override;
-  void fetch_marked(T* host_dst, const T* mb, size_t count) override;
+  bool deferred_ok() const override { return true; }
+  void set_stop_flag(T* stop) override { stop_ = stop; }
+  void start_step_gated(int64_t n, const StepGate<T>& g, const T* resid, T* vj, T* out_x, T* bx) override;
   void ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) override;
 
   void dots(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out) override;
@@ -133,6 +132,7 @@ class CudaVecOps final : public VecOps<T> {
     return partial_;
   }
   unsigned int* reduction_ticket() { return ticket_; }
+  const T* stop_flag() const { return stop_; }
 
  private:
   cudaStream_t stream_;
@@ -143,10 +143,8 @@ class CudaVecOps final : public VecOps<T> {
   T* mb_dev_ = nullptr;
   size_t mb_count_ = 0;
   T* mb_pinned_ = nullptr;
-  // side stream + event for fetch_marked(): the mailbox copy overlaps kernels enqueued after the mark
-  cudaStream_t copy_stream_ = nullptr;
-  cudaEvent_t mark_event_ = nullptr;
-  bool marked_ = false;
+  // sticky stop flag of a device-resident sweep (mailbox entry, 0 = run); checked by every step kernel
+  T* stop_ = nullptr;
   // two-stage reduction scratch: partial_[grid][pcols_] and a ticket counter
   T* partial_ = nullptr;
   size_t partial_count_ = 0;
@@ -156,9 +154,6 @@ class CudaVecOps final : public VecOps<T> {
   size_t qbuf_count_ = 0;
   T* qpinned_ = nullptr;
   size_t qpinned_count_ = 0;
-  // cached TMA descriptors for the fast path (opaque storage, see vecops_tma.cu)
-  struct TmaCache;
-  TmaCache* tma_ = nullptr;
 
   void ensure_partial(size_t count);
   T* stage_matrix(const T* host, int rows, int cols, int ld);  // -> device, packed rows x cols, column-major
@@ -175,7 +170,6 @@ class CudaVecOps final : public VecOps<T> {
   bool dots_tma(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out);
   bool vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* qdev, T* out, int64_t ldo,
               bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2);
-  void tma_release();
 };
 
 }  // namespace ab200

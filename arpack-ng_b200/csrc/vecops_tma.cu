@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "gate.cuh"
 #include "tma_common.cuh"
 #include "vecops_cuda.cuh"
 
@@ -58,12 +59,14 @@ struct OrthParams {
   const T* pred_w2;
   const T* pred_r2;
   T* flag_out;
+  const T* stop;  // sticky stop flag of a device-resident sweep (may be null)
 };
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreadsTma, 1)
 k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
+  if (stopped(p.stop)) return;
   if (MODE == UPD && p.pred_w2 != nullptr) {
     // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
     const T wn = sqrt(*p.pred_w2), rn = sqrt(*p.pred_r2);
@@ -250,6 +253,7 @@ template <typename T, bool SPEC, int KB>
 __global__ void __launch_bounds__(kThreadsTma, 1)
 k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
+  if (stopped(p.stop)) return;
   if (!SPEC && p.pred_w2 != nullptr) {
     // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
     const T wn = sqrt(*p.pred_w2), rn = sqrt(*p.pred_r2);
@@ -657,9 +661,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 template <typename T>
-struct CudaVecOps<T>::TmaCache {};
-
-template <typename T>
 bool CudaVecOps<T>::fast_path_ok(int64_t n, int j, const T* v, int64_t ldv) const {
   if (j < 1 || j > MAXB * CB || n < 1) return false;
   if (!aligned16(v)) return false;                                     // TMA: 16-byte aligned base ...
@@ -676,7 +677,7 @@ bool CudaVecOps<T>::dots_tma(int64_t n, int j, const T* v, int64_t ldv, const T*
   const int grid = (int)std::min<int64_t>((n + R - 1) / R, num_sms_);
   p.pcols = j + 1;
   ensure_partial((size_t)grid * p.pcols);
-  p.x = x; p.y = y; p.partial = partial_; p.out = out; p.ticket = ticket_;
+  p.x = x; p.y = y; p.partial = partial_; p.out = out; p.ticket = ticket_; p.stop = stop_;
   return launch_orth<T, DOTS>(stream_, num_sms_, v, ldv, p, "dots_tma",
                               (double)sizeof(T) * n * (j + (x == y ? 1.0 : 2.0)));
 }
@@ -692,7 +693,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     p.n = n;
     geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
-    p.x = w; p.y = w; p.partial = partial_; p.out = mbA; p.ticket = ticket_;
+    p.x = w; p.y = w; p.partial = partial_; p.out = mbA; p.ticket = ticket_; p.stop = stop_;
     if (!launch_orth<T, DOTS>(stream_, num_sms_, v, ldv, p, "dots_tma", (double)sizeof(T) * n * (j + 1.0)))
       return false;
   }
@@ -703,7 +704,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     p.n = n;
     geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
-    p.x = w; p.dst = resid; p.coef = mbA; p.partial = partial_; p.out = mbB; p.ticket = ticket_;
+    p.x = w; p.dst = resid; p.coef = mbA; p.partial = partial_; p.out = mbB; p.ticket = ticket_; p.stop = stop_;
     if (!launch_upd<T, true>(stream_, num_sms_, v, ldv, p, "update_spec_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("update_spec_tma launch failed after dots_tma succeeded");
   }
@@ -715,7 +716,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     geometry<T>(j, aligned16(resid), p);
     p.pcols = 1;
     p.x = resid; p.dst = resid; p.coef = mbB; p.partial = partial_; p.out = mbC; p.ticket = ticket_;
-    p.pred_w2 = mbA + j; p.pred_r2 = mbB + j; p.flag_out = mbC + 1;
+    p.pred_w2 = mbA + j; p.pred_r2 = mbB + j; p.flag_out = mbC + 1; p.stop = stop_;
     if (!launch_upd<T, false>(stream_, num_sms_, v, ldv, p, "reorth_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("reorth_tma launch failed after dots_tma succeeded");
   }
@@ -773,11 +774,6 @@ bool CudaVecOps<T>::vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv
   AB200_CUDA_CHECK(cudaGetLastError());
   return true;
 }
-template <typename T>
-void CudaVecOps<T>::tma_release() {}
-
-template struct CudaVecOps<double>::TmaCache;
-template struct CudaVecOps<float>::TmaCache;
 template bool CudaVecOps<double>::fast_path_ok(int64_t, int, const double*, int64_t) const;
 template bool CudaVecOps<float>::fast_path_ok(int64_t, int, const float*, int64_t) const;
 template bool CudaVecOps<double>::orth_step_tma(int64_t, int, const double*, int64_t, const double*, double*, double*, double*, double*);
@@ -786,7 +782,5 @@ template bool CudaVecOps<double>::dots_tma(int64_t, int, const double*, int64_t,
 template bool CudaVecOps<float>::dots_tma(int64_t, int, const float*, int64_t, const float*, const float*, float*);
 template bool CudaVecOps<double>::vq_tma(int64_t, int, int, const double*, int64_t, const double*, double*, int64_t, bool, double, double, int, double*, double*);
 template bool CudaVecOps<float>::vq_tma(int64_t, int, int, const float*, int64_t, const float*, float*, int64_t, bool, float, float, int, float*, float*);
-template void CudaVecOps<double>::tma_release();
-template void CudaVecOps<float>::tma_release();
 
 }  // namespace ab200

@@ -159,8 +159,8 @@ class Oracle:
                  C.byref(info))
             if ido.value in (-1, 1):
                 x = workd[ipntr[0] - 1: ipntr[0] - 1 + n]
-                if mode == 2 and ido.value == 1:
-                    y, ax = op(x)  # mode 2: op returns (M^-1 A x, A x); x is overwritten with A x
+                if mode == 2 and ido.value == 1 and sym:
+                    y, ax = op(x)  # dsaupd mode 2: op returns (M^-1 A x, A x); x is overwritten with A x
                     workd[ipntr[0] - 1: ipntr[0] - 1 + n] = ax
                     workd[ipntr[1] - 1: ipntr[1] - 1 + n] = y
                 elif mode == 5:
@@ -323,8 +323,8 @@ def hostdouble_lib():
         L.hd_set_registered_op.argtypes = [C.c_void_p, C.c_int, OP_FN, C.c_int, C.c_int]
         L.hd_fused_dot_maxdiff.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hd_fused_dot_maxdiff.restype = C.c_double
-        L.hd_speculative_hits.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.hd_speculative_hits.restype = C.c_longlong
+        L.hd_deferred_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        L.hd_set_deferral.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for p, rp, rt in (("d", c_dbl_p, C.c_double), ("s", c_flt_p, C.c_float)):
             for fam in ("s", "n"):
                 f = getattr(L, f"hd_{p}{fam}aupd")
@@ -407,9 +407,16 @@ class HostDouble(Oracle):
         self._opcb = OP_FN(cb) if op is not None else C.cast(None, OP_FN)
         self.L.hd_set_registered_op(self._procs[isd], int(isd), self._opcb, n, int(fused))
 
-    def speculative_hits(self, sym=True, dtype=np.float64):
+    def deferred_stats(self, sym=True, dtype=np.float64):
+        """(steps run inside device-resident batches, batches cut short by a rare path, host round trips)."""
         isd = np.dtype(dtype) == np.float64
-        return int(self.L.hd_speculative_hits(self._procs[isd], int(isd), int(sym)))
+        out = (C.c_longlong * 3)()
+        self.L.hd_deferred_stats(self._procs[isd], int(isd), int(sym), out)
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def set_deferral(self, on, dtype=np.float64):
+        isd = np.dtype(dtype) == np.float64
+        self.L.hd_set_deferral(self._procs[isd], int(isd), int(on))
 
     def fused_dot_maxdiff(self, sym=True, dtype=np.float64):
         isd = np.dtype(dtype) == np.float64

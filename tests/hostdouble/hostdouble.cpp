@@ -83,6 +83,7 @@ struct HostVecOps final : VecOps<T> {
   }
   void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
   void start_step(int64_t n, T inv, const T* resid, T* vj, T* outx, T* bx, bool from_resid) override {
+    if (halted()) return;
     for (int64_t i = 0; i < n; ++i) {
       const T t = resid[i] * inv;
       vj[i] = t;
@@ -90,13 +91,25 @@ struct HostVecOps final : VecOps<T> {
       if (bx) bx[i] = from_resid ? t : bx[i] * inv;
     }
   }
-  unsigned long long spec_calls = 0;
-  bool start_step_speculative(int64_t n, int j, const T* mbB, const T* mbC, T tiny, const T* resid, T* vj, T* outx,
-                              T* bx) override {
-    ++spec_calls;
-    const T val = (mbC[1] != T(0)) ? mbC[0] : mbB[j];
-    const T rn = std::sqrt(val);
-    if (!(rn >= tiny) || !(rn > T(0))) return true;
+  // device-resident sweep emulation: kernels "run" at once, so the sticky stop flag is simply read here
+  T* stop_ = nullptr;
+  unsigned long long gated_calls = 0;
+  bool halted() const { return stop_ != nullptr && *stop_ != T(0); }
+  bool deferred_ok() const override { return true; }
+  void set_stop_flag(T* stop) override { stop_ = stop; }
+  void start_step_gated(int64_t n, const StepGate<T>& g, const T* resid, T* vj, T* outx, T* bx) override {
+    ++gated_calls;
+    if (g.stop != nullptr && *g.stop != T(0)) return;
+    const T wn = std::sqrt(g.A[g.prev_j]);
+    T rn = std::sqrt(g.B[g.prev_j]);
+    bool ok = true;
+    if (!(rn > (T)0.717f * wn)) {
+      const T rn1 = std::sqrt(g.C[0]);
+      if (rn1 > (T)0.717f * rn) rn = rn1;
+      else ok = false;
+    }
+    if (!(rn >= g.tiny) || !(rn > T(0))) ok = false;
+    if (!ok) { *g.stop = g.stop_code; return; }
     const T inv = T(1) / rn;
     for (int64_t i = 0; i < n; ++i) {
       const T t = resid[i] * inv;
@@ -104,7 +117,6 @@ struct HostVecOps final : VecOps<T> {
       outx[i] = t;
       if (bx) bx[i] = t;
     }
-    return true;
   }
   void ger(int64_t n, int k, const T* resid, const T* w, T* z, int64_t ldz) override {
     for (int c = 0; c < k; ++c)
@@ -134,6 +146,7 @@ struct HostVecOps final : VecOps<T> {
     if (nrm2) *nrm2 = s;
   }
   void orth_step(int64_t n, int j, const T* v, int64_t ldv, const T* w, T* resid, T* A, T* B, T* C) override {
+    if (halted()) return;
     dots(n, j, v, ldv, w, w, A);
     allreduce_sum(A, (size_t)j + 1);
     update(n, j, v, ldv, A, w, resid, nullptr);
@@ -200,6 +213,7 @@ struct Proc {  // one "process": SAVE'd seed etc.
   std::unique_ptr<IrlSym<T>> sym;
   std::unique_ptr<IrlNonsym<T>> nonsym;
   // registered-operator mode (IrlBase::set_registered_op): y = OP x through a C callback, no ido = +-1 hand-offs
+  bool defer = true;
   op_fn reg_op = nullptr;
   int reg_fused = 0;
   int reg_n = 0;
@@ -215,7 +229,23 @@ struct Proc {  // one "process": SAVE'd seed etc.
       return;
     }
     // host emulation of the fused SpMV: vj = inv*resid, y = OP vj, dots {vj.y, y.y}
-    s->set_registered_op(plain, [f, n](T inv, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+    HostVecOps<T>* o = &ops;
+    s->set_registered_op(plain, [f, n, o](T inv, const StepGate<T>* g, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+      if (o->halted()) return true;
+      if (g != nullptr) {
+        // the gate of the fused kernel: same tests as start_step_gated, on a scratch pass that writes nothing
+        const T wn = std::sqrt(g->A[g->prev_j]);
+        T rn = std::sqrt(g->B[g->prev_j]);
+        bool ok = true;
+        if (!(rn > (T)0.717f * wn)) {
+          const T rn1 = std::sqrt(g->C[0]);
+          if (rn1 > (T)0.717f * rn) rn = rn1;
+          else ok = false;
+        }
+        if (!(rn >= g->tiny) || !(rn > T(0))) ok = false;
+        if (!ok) { *g->stop = g->stop_code; return true; }
+        inv = T(1) / rn;
+      }
       for (int i = 0; i < n; ++i) vj[i] = inv * resid[i];
       f((const void*)vj, (void*)y, n);
       T a = 0, b = 0;
@@ -249,10 +279,18 @@ double hd_fused_dot_maxdiff(void* p, int is_double, int fam_sym) {
   auto* q = (Proc<float>*)p;
   return fam_sym ? q->sym->fused_dot_maxdiff : q->nonsym->fused_dot_maxdiff;
 }
-long long hd_speculative_hits(void* p, int is_double, int fam_sym) {
-  if (is_double) { auto* q = (Proc<double>*)p; return fam_sym ? q->sym->speculative_hits() : q->nonsym->speculative_hits(); }
-  auto* q = (Proc<float>*)p;
-  return fam_sym ? q->sym->speculative_hits() : q->nonsym->speculative_hits();
+// out3 = {steps that ran inside device-resident batches, batches cut short by a rare path, host round trips}
+void hd_deferred_stats(void* p, int is_double, int fam_sym, long long* out3) {
+#define HD_DS(Q) do { if (fam_sym) { out3[0] = Q->sym->deferred_steps(); out3[1] = Q->sym->deferred_trips(); out3[2] = Q->sym->host_round_trips(); } \
+                      else { out3[0] = Q->nonsym->deferred_steps(); out3[1] = Q->nonsym->deferred_trips(); out3[2] = Q->nonsym->host_round_trips(); } } while (0)
+  if (is_double) { auto* q = (Proc<double>*)p; HD_DS(q); }
+  else { auto* q = (Proc<float>*)p; HD_DS(q); }
+#undef HD_DS
+}
+// deferral needs hand-off slots the "device" reaches by itself: the double's arrays always qualify
+void hd_set_deferral(void* p, int is_double, int on) {
+  if (is_double) ((Proc<double>*)p)->defer = on != 0;
+  else ((Proc<float>*)p)->defer = on != 0;
 }
 // COMMON /debug/ of the control code under test (what debug_c does in the product, api.cu)
 void hd_debug(const int* levels24) { std::memcpy(static_cast<void*>(&trace_levels()), levels24, sizeof(TraceLevels)); }
@@ -272,6 +310,8 @@ void hd_stats(void* p, int is_double, int fam_sym, int* out5) {
       else q->nonsym.reset(new IrlNonsym<T>(&q->ops, q->par, &q->seed, &q->smlnum_first));                       \
       if (ISSYM) q->attach(q->sym.get());                                                                        \
       else q->attach(q->nonsym.get());                                                                           \
+      if (ISSYM) q->sym->set_deferral(q->defer);                                                                 \
+      else q->nonsym->set_deferral(q->defer);                                                                    \
     }                                                                                                            \
     if (ISSYM) q->sym->aupd(ido, bmat[0], n, which, nev, tol, resid, ncv, v, ldv, iparam, ipntr, workd, workl,   \
                             lworkl, info);                                                                       \

@@ -102,6 +102,29 @@ def test_registered_operator_under_a_communicator(ab_comm):
         hijack()
 
 
+def test_pdseupd_rvec0_shift_invert_does_not_touch_z(ab_comm):
+    """pdseupd_c with rvec = 0 in mode 3: eigenvalues only.  The reference's pdseupd.f:858 runs its rank-1
+    purification update even then; here z is not mapped without rvec, so the update must be skipped (it used to
+    write through a null device pointer and poison the CUDA context).  Values equal the rvec = 1 run's."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    ab, comm = ab_comm
+    S = laplace2d(19, 17).tocsc()
+    n, sigma = S.shape[0], 0.9
+    lu = spla.splu((S - sigma * sp.identity(n)).tocsc())
+    r0 = np.random.default_rng(12).uniform(-1, 1, n)
+
+    def op(x, y, *_):
+        y[:] = lu.solve(np.ascontiguousarray(x))
+    kw = dict(tol=1e-10, mxiter=2000, mode=3, sigma=sigma, resid=r0, comm=comm, host_buffers=True)
+    a = ab.solve(op, n, 4, 16, "LM", rvec=True, **kw)
+    b = ab.solve(op, n, 4, 16, "LM", rvec=False, **kw)
+    assert a.info == b.info == 0 and a.ierr == b.ierr == 0
+    assert np.abs(np.sort(a.d) - np.sort(b.d)).max() <= 1e-12 * np.abs(a.d).max()
+    import torch
+    torch.cuda.synchronize()     # a faulting k_ger would surface here as a sticky error
+
+
 def test_multi_gpu_check_under_torchrun_when_available():
     import torch
     ngpu = torch.cuda.device_count()

@@ -353,25 +353,56 @@ def test_registered_operator_is_ignored_outside_mode1():
 
 
 @pytest.mark.parametrize("sym", [True, False])
-def test_speculative_start_of_step_hits_and_changes_nothing(sym):
-    """K1+K2 of step j+1 are issued before the host has read step j's mailbox (IrlBase::extend); the scale is taken
-    from the mailbox.  Every step but the first of each sweep must be served that way, with results identical to the
-    oracle's (counts) -- the speculation is invisible."""
+@pytest.mark.parametrize("registered", [False, True])
+def test_device_resident_sweeps_change_nothing(sym, registered):
+    """IrlBase::extend, deferred mode: a whole sweep of steps is enqueued without a host round trip (each step has its
+    own mailbox slot, the next step's scale and the rare-path tests are formed from the slot by the gated start of
+    step) and the host replays its bookkeeping once per sweep.  Path and results must be those of the synchronous
+    mode and of the oracle, with one round trip per sweep instead of one per step."""
     if sym:
         A, nev, ncv, which = laplace2d(19, 16), 4, 16, "LA"
     else:
         A, nev, ncv, which = convdiff2d(15, rho=10.0), 4, 16, "LM"
     n = A.shape[0]
     r0 = start(n, 5)
-    hd = HostDouble()
+    hd, hs = HostDouble(), HostDouble()
+    hs.set_deferral(False)
+    if registered:
+        hd.register_op(lambda x: A @ x, n, fused=True)
+        hs.register_op(lambda x: A @ x, n, fused=True)
     a = hd.solve(lambda x: A @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
+    s = hs.solve(lambda x: A @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
     b = Oracle().solve(lambda x: A @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=500, resid=r0)
-    assert a.info == b.info == 0 and counts(a) == counts(b)
-    hits = hd.speculative_hits(sym)
+    assert a.info == b.info == s.info == 0 and counts(a) == counts(b) == counts(s)
+    assert np.array_equal(a.workl, s.workl)           # bit-identical projected problem
+    steps, trips, trips_rt = hd.deferred_stats(sym)
     nopx, sweeps = int(a.iparam[8]), int(a.iparam[2]) + 1
-    # every step except the first of a sweep (and the start-vector product) can be speculated
-    assert nopx - 2 * sweeps - 2 <= hits <= nopx
-    assert hits > nopx // 2
+    assert trips == 0
+    assert steps >= nopx - 1                          # everything but the start-vector product ran deferred
+    assert trips_rt <= 3 * sweeps + 4                 # one block read per sweep (+ the restart norm, + getv0)
+    assert hs.deferred_stats(sym)[0] == 0 and hs.deferred_stats(sym)[2] >= nopx - 1
+
+
+def test_device_resident_sweep_is_cut_short_by_a_breakdown():
+    """Start vector inside a 3-dimensional invariant subspace: rnorm collapses in the middle of a sweep.  The gated
+    start of the next step trips, every later kernel of the batch exits at once, and the host resumes with the
+    reference's restart logic (dsaitr.f:378-427) from exactly that step -- same path as the oracle and as the
+    synchronous mode."""
+    n = 60
+    diag = np.arange(1, n + 1, dtype=float)
+    r0 = np.zeros(n)
+    r0[[3, 17, 41]] = [1.0, -2.0, 0.5]
+    hd, hs = HostDouble(), HostDouble()
+    hs.set_deferral(False)
+    a = hd.solve(lambda x: diag * x, n, 4, 12, "LM", tol=1e-10, mxiter=500, resid=r0)
+    s = hs.solve(lambda x: diag * x, n, 4, 12, "LM", tol=1e-10, mxiter=500, resid=r0)
+    b = Oracle().solve(lambda x: diag * x, n, 4, 12, "LM", tol=1e-10, mxiter=500, resid=r0)
+    assert b.stats["nrstrt"] > 0
+    assert counts(a) == counts(s)
+    assert a.info == b.info and a.stats["nrstrt"] == b.stats["nrstrt"] and a.nconv == b.nconv
+    assert np.array_equal(a.workl, s.workl)
+    assert hd.deferred_stats()[1] >= 1                # at least one batch was cut short
+    assert np.abs(np.sort(a.d) - np.sort(b.d)).max() < 1e-8
 
 
 def _buckling_cayley_problem(n=80):
