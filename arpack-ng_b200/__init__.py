@@ -105,6 +105,7 @@ def lib():
     L.ab200_release.argtypes = [vp]
     L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.ab200_device_count.restype = C.c_int
+    L.ab200_host_round_trips.restype = C.c_ulonglong
     L.ab200_register_csr_op_f64.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
     L.ab200_register_csr_op_f32.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp]
     L.ab200_register_csr_halo_op_f64.argtypes = [vp, C.c_int, C.c_int, C.c_longlong, vp, vp, vp, C.c_int, C.c_int, vp]
@@ -145,6 +146,11 @@ def launch_stats():
     out = (C.c_ulonglong * 4)()
     lib().ab200_launch_stats(out)
     return {"kernels": int(out[0]), "allreduces": int(out[1]), "tma_path": int(out[2]), "generic_path": int(out[3])}
+
+
+def host_round_trips():
+    """Blocking device->host mailbox reads since the library was loaded."""
+    return int(lib().ab200_host_round_trips())
 
 
 def profile(enable=None, reset=False):

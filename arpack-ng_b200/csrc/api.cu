@@ -562,6 +562,7 @@ void ab200_launch_stats(unsigned long long* out4) {
   const LaunchStats& s = launch_stats();
   out4[0] = s.kernels; out4[1] = s.allreduces; out4[2] = s.fast_path; out4[3] = s.fallback;
 }
+unsigned long long ab200_host_round_trips(void) { return launch_stats().fetches; }
 void ab200_reset_seed(void) {
   Globals<double>::seed = SeedState(); Globals<double>::seed_par = SeedState();
   Globals<float>::seed = SeedState(); Globals<float>::seed_par = SeedState();

@@ -541,6 +541,7 @@ void CudaVecOps<T>::fetch(T* host_dst, const T* mb, size_t count) {
   const size_t off = (size_t)(mb - mb_dev_);
   AB200_CUDA_CHECK(cudaMemcpyAsync(mb_pinned_ + off, mb, sizeof(T) * count, cudaMemcpyDeviceToHost, stream_));
   AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  launch_stats().fetches++;
   std::memcpy(host_dst, mb_pinned_ + off, sizeof(T) * count);
 }
 template <typename T>

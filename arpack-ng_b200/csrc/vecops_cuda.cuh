@@ -35,6 +35,7 @@ struct LaunchStats {
   unsigned long long allreduces = 0;
   unsigned long long fast_path = 0;   // launches of the TMA-tiled kernels
   unsigned long long fallback = 0;    // launches of the generic kernels on the tall-skinny ops
+  unsigned long long fetches = 0;     // blocking device->host mailbox reads (host round trips)
 };
 LaunchStats& launch_stats();
 

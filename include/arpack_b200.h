@@ -199,6 +199,9 @@ void ab200_release(const void* workl);
 void ab200_release_all(void);
 /* out4 = {kernels launched, all-reduces issued, TMA-path launches, generic-path launches} since load */
 void ab200_launch_stats(unsigned long long* out4);
+/* blocking device->host mailbox reads since load: one per Lanczos/Arnoldi step in the synchronous mode, one per sweep
+   when the sweep runs device-resident (IrlBase::extend) */
+unsigned long long ab200_host_round_trips(void);
 /* forget the SAVE'd dgetv0 seed / dnaitr smlnum, as if the process had just started */
 void ab200_reset_seed(void);
 /* Registered-operator mode (opt-in; strict RCI stays the default): the library applies y = A x (square CSR matrix in
