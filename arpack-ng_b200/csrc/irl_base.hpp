@@ -8,7 +8,9 @@
 //   extend()        <->  SRC/dsaitr.f:204-853 and SRC/dnaitr.f:209-840 (+ pdsaitr.f / pdnaitr.f)
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -55,6 +57,33 @@ struct Counters {
   int nopx = 0, nbx = 0, nrorth = 0, nitref = 0, nrstrt = 0;
 };
 
+// Host-side phase clock (diagnostic, AB200_TIMING=1): where the host spends its time inside the library during a solve.
+// The reference's own timers (stat.h t*) are dead in arpack-ng builds (UTIL/second_NONE.f); this is not a replacement
+// for them, it only answers "is the device waiting for the host, and where".
+struct PhaseClock {
+  enum { FETCH_LOG, REPLAY, PROJECTED, SHIFTS, RESTART_ENQ, FETCH_NORM, STEP_ENQ, NPHASE };
+  double acc[NPHASE] = {0, 0, 0, 0, 0, 0, 0};
+  long long cnt[NPHASE] = {0, 0, 0, 0, 0, 0, 0};
+  bool on = false;
+  PhaseClock() { on = getenv("AB200_TIMING") != nullptr; }
+  static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  struct Scope {
+    PhaseClock* pc; int ph; double t0;
+    Scope(PhaseClock* p, int phase) : pc(p->on ? p : nullptr), ph(phase), t0(pc ? now() : 0.0) {}
+    ~Scope() { if (pc) { pc->acc[ph] += now() - t0; pc->cnt[ph]++; } }
+  };
+  void dump(const char* what) const {
+    if (!on) return;
+    static const char* nm[NPHASE] = {"fetch_log(blocked)", "replay", "projected_eig", "select+shifts+qr", "restart_enqueue",
+                                     "fetch_norm(blocked)", "step_enqueue"};
+    std::fprintf(stderr, "arpack_b200 timing [%s]:", what);
+    for (int i = 0; i < NPHASE; ++i) std::fprintf(stderr, " %s=%.3fms/%lld", nm[i], 1e3 * acc[i], cnt[i]);
+    std::fprintf(stderr, "\n");
+  }
+};
+
 // LAPACK xLARNV seed, SAVE'd across solves in the reference (dgetv0.f:164,202-208); one per precision
 struct SeedState {
   bool inited = false;
@@ -68,6 +97,7 @@ class IrlBase {
   virtual ~IrlBase() {}
 
   Counters cnt;
+  PhaseClock phase_clock;
   const Counters& counters() const { return cnt; }
   // largest relative disagreement between the SpMV-epilogue dots and the CGS sweep (registered-operator mode)
   T fused_dot_maxdiff = 0;
@@ -157,6 +187,8 @@ class IrlBase {
   T gv_rnorm0_ = 0, rnorm_ = 0;
 
   T fetch_norm_from_dot(T* mbslot) {
+    PhaseClock::Scope pcs(&phase_clock, PhaseClock::FETCH_NORM);
+    cnt_round_trips_++;
     ops_->allreduce_sum(mbslot, 1);
     ops_->fetch(hC(), mbslot, 1);
     return std::sqrt(std::fabs(hC()[0]));
@@ -349,6 +381,7 @@ class IrlBase {
         ops_->set_stop_flag(mb_stop());
         for (df_j_ = df_first_; df_j_ <= df_last_; ++df_j_) {
           {
+            PhaseClock::Scope pcs(&phase_clock, PhaseClock::STEP_ENQ);
             const int s = df_j_ - df_first_ + 1;
             T* sC = slot_dev(s) + 2 * seg_;
             StepGate<T> g;
@@ -374,12 +407,16 @@ class IrlBase {
             CO_YIELD(ai_pc_);
           }
           {
+            PhaseClock::Scope pcs(&phase_clock, PhaseClock::STEP_ENQ);
             T* sA = slot_dev(df_j_ - df_first_ + 1);
             ops_->orth_step(n_, df_j_, v_, ldv_, slot(irj()), resid_, sA, sA + seg_, sA + 2 * seg_);
           }
         }
         ops_->set_stop_flag(nullptr);
-        ops_->fetch(logh_.data(), mb_stop(), (size_t)4 + (size_t)3 * seg_ * (df_last_ - df_first_ + 1));
+        {
+          PhaseClock::Scope pcs(&phase_clock, PhaseClock::FETCH_LOG);
+          ops_->fetch(logh_.data(), mb_stop(), (size_t)4 + (size_t)3 * seg_ * (df_last_ - df_first_ + 1));
+        }
         cnt_round_trips_++;
         // replay: the host logic of every step, in order, from the step's own mailbox slot
         for (; ai_j_ <= df_last_; ++ai_j_) {

@@ -84,6 +84,7 @@ class IrlSym : public IrlBase<T> {
       return;
     }
     *ido = 99;
+    this->phase_clock.dump("dsaupd");
     iparam[2] = mxiter_out_;
     iparam[4] = np_;
     iparam[8] = cnt.nopx; iparam[9] = cnt.nbx; iparam[10] = cnt.nrorth;
@@ -425,7 +426,12 @@ class IrlSym : public IrlBase<T> {
       this->ai_k_ = nev_; this->ai_np_ = np_;
       CO_CALL(pc_, this->extend());
       if (this->ai_info_ > 0) { fail_no_factorisation(); CO_END_EARLY(pc_); }
-      if (ritz_bounds() != 0) {
+      int rb_ierr;
+      {
+        PhaseClock::Scope pcs(&this->phase_clock, PhaseClock::PROJECTED);
+        rb_ierr = ritz_bounds();
+      }
+      if (rb_ierr != 0) {
         info_ = -8;
         mxiter_out_ = mxiter_;
         CO_END_EARLY(pc_);
@@ -466,10 +472,14 @@ class IrlSym : public IrlBase<T> {
         std::copy(wrk(), wrk() + np_, ritz());
       }
       // implicit restart: host QR sweeps, then V <- V*Q, r <- sigma*r + beta*v_{kev+1}, ||r|| in one pass
-      qr_sweeps(nev_, np_, ritz());
+      {
+        PhaseClock::Scope pcs(&this->phase_clock, PhaseClock::SHIFTS);
+        qr_sweeps(nev_, np_, ritz());
+      }
       sigmak_ = Q(kplusp_, nev_);
       betak_ = H(nev_ + 1, 1);
       {
+        PhaseClock::Scope pcs(&this->phase_clock, PhaseClock::RESTART_ENQ);
         const bool has_beta = betak_ > T(0);
         ops_->vq_update(n_, kplusp_, nev_ + (has_beta ? 1 : 0), v_, ldv_, wl_ + iq_, ldq_, true, sigmak_,
                         has_beta ? betak_ : T(0), has_beta ? nev_ : -1, resid_, bmat_ == 'I' ? mbC() : nullptr);

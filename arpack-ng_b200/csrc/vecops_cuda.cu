@@ -56,10 +56,30 @@ void Profiler::end(cudaStream_t s) {
   if (pending_.size() >= 8192) flush();
 }
 void Profiler::flush() {
+  // "(between launches)": device time from the end of one profiled launch to the start of the next one on the same
+  // stream -- copies, memsets, un-profiled kernels and genuine idle time (the host not keeping the queue fed)
+  int gap_idx = -1;
+  if (pending_.size() > 1) {
+    static const char* kGap = "(between launches)";
+    for (size_t i = 0; i < table_.size(); ++i)
+      if (table_[i].name == kGap) gap_idx = (int)i;
+    if (gap_idx < 0) {
+      table_.push_back(KernelProfile{kGap, 0ULL, 0.0, 0.0});
+      gap_idx = (int)table_.size() - 1;
+    }
+  }
+  cudaEvent_t prev_end = nullptr;
   for (auto& p : pending_) {
     float ms = 0.f;
     cudaEventSynchronize(p.e1);
     if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) table_[p.idx].ms += ms;
+    if (prev_end != nullptr && gap_idx >= 0 && cudaEventElapsedTime(&ms, prev_end, p.e0) == cudaSuccess && ms < 50.f) {
+      table_[gap_idx].ms += ms;   // (gaps above 50 ms are pauses between solves, not part of one)
+      table_[gap_idx].launches++;
+    }
+    prev_end = p.e1;
+  }
+  for (auto& p : pending_) {
     pool_.push_back(p.e0);
     pool_.push_back(p.e1);
   }
