@@ -126,6 +126,8 @@ def lib():
     L.ab200_nccl_unique_id.argtypes = [vp]
     L.ab200_comm_create.argtypes = [vp, C.c_int, C.c_int]
     L.ab200_comm_destroy.argtypes = [C.c_int]
+    L.ab200_comm_halo_buffer.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+    L.ab200_comm_halo_buffer.restype = vp
     L.ab200_csr_spmv_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp]
     L.ab200_csr_spmv_f32.argtypes = [C.c_int, vp, vp, vp, vp, vp]
     L.ab200_csr_spmv_hostvec_f64.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp]
@@ -327,7 +329,7 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             rc = L.ab200_register_csr_halo_op_f64(workl.ctypes.data, comm, registered_op.n, registered_op.nnz,
                                                   registered_op.rowptr.data_ptr(), registered_op.col.data_ptr(),
                                                   registered_op.val.data_ptr(), registered_op.halo_lo,
-                                                  registered_op.halo_hi, registered_op.halo.data_ptr())
+                                                  registered_op.halo_hi, registered_op.halo_address(comm))
         else:
             reg = L.ab200_register_csr_op_f64 if np_dt == np.float64 else L.ab200_register_csr_op_f32
             # device tensors are used in place; host arrays (HostCsr) are uploaded once by the library at ido = 0
@@ -590,16 +592,28 @@ class CsrOperator:
         if f(*self._spmv_args, xptr, yptr) != 0:
             raise ArpackB200Error("csr_spmv failed")
 
+    def halo_address(self, comm):
+        """Where the neighbours' planes arrive.  The first use under a communicator is COLLECTIVE: the communicator is
+        asked for its own halo buffer (ab200_comm_halo_buffer: the neighbours then store their planes straight into it
+        over NVLink); without peer memory the operator's ordinary device buffer is used (ncclSend/ncclRecv)."""
+        if getattr(self, "_halo_comm", None) != comm:
+            self._halo_comm = comm
+            self._halo_ptr = None
+            if self.halo_lo + self.halo_hi > 0:
+                p = lib().ab200_comm_halo_buffer(comm, self.halo_lo, self.halo_hi, self.val.element_size())
+                self._halo_ptr = p if p else None
+        return self._halo_ptr if self._halo_ptr is not None else self.halo.data_ptr()
+
     def apply_halo_ptr(self, comm, xptr, yptr):
         if lib().ab200_csr_spmv_halo_f64(comm, self.n, self.halo_lo, self.halo_hi, self.rowptr.data_ptr(),
                                         self.col.data_ptr(), self.val.data_ptr(), xptr, yptr,
-                                        self.halo.data_ptr()) != 0:
+                                        self.halo_address(comm)) != 0:
             raise ArpackB200Error("csr_spmv_halo failed")
 
     def apply_halo(self, comm, x, y):
         rc = lib().ab200_csr_spmv_halo_f64(comm, self.n, self.halo_lo, self.halo_hi, self.rowptr.data_ptr(),
                                           self.col.data_ptr(), self.val.data_ptr(), x.data_ptr(), y.data_ptr(),
-                                          self.halo.data_ptr())
+                                          self.halo_address(comm))
         if rc != 0:
             raise ArpackB200Error(f"csr_spmv_halo failed ({rc})")
 

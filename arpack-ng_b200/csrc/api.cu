@@ -187,6 +187,16 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
         if (csr_op_apply<T>(d, x, y) != 0) throw CudaError("registered CSR operator: SpMV launch failed");
       },
       [d, ops](T inv, const StepGate<T>* gate, const T* resid, T* vj, T* y, T* mb_dots) -> bool {
+        if (!csr_op_fusable<T>(d)) return false;  // long rows: start_step + plain SpMV
+        // multi-GPU: a gated product finishes the fused reduction of ||r'||^2 itself (CudaVecOps::attach_pending)
+        StepGate<T> g;
+        if (gate != nullptr) {
+          g = *gate;
+          ops->attach_pending(g);
+          gate = &g;
+        } else {
+          ops->resolve_pending();
+        }
         const int rc = csr_op_apply_fused<T>(d, inv, gate, ops->stop_flag(), resid, vj, y,
                                              ops->reduction_scratch(2 * 148 * 16), mb_dots, ops->reduction_ticket());
         if (rc < 0) throw CudaError("registered CSR operator: fused SpMV launch failed");

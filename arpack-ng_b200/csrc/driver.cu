@@ -22,6 +22,8 @@ namespace ab200 {
 NcclComm* comm_from_handle(int handle);
 void nccl_halo_exchange(NcclComm* c, const void* send_lo, void* recv_lo, size_t n_lo, const void* send_hi,
                         void* recv_hi, size_t n_hi, bool is_double, cudaStream_t s);
+bool nccl_halo_is_peer_buffer(const NcclComm* c, const void* buf);
+const void* nccl_halo_exchange_peer(NcclComm* c, const void* send_lo, const void* send_hi, cudaStream_t s);
 
 namespace {
 
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(ROWS) k_csr_spmv_stream(int nrows, const int* 
   __shared__ T prod[CAP];
   if (FUSED) {
     if (stopped(stop)) return;
-    if (gate.stop != nullptr && !gate_eval(gate, xs)) {
+    if (gate.stop != nullptr && !gate_eval_block(gate, xs)) {
       if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
       return;
     }
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
   constexpr int CAP = ROWS * EPT;  // entries per ring slot, alignment pad included
   if (FUSED) {
     if (stopped(stop)) return;
-    if (gate.stop != nullptr && !gate_eval(gate, xs)) {
+    if (gate.stop != nullptr && !gate_eval_block(gate, xs)) {
       if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
       return;
     }
@@ -669,26 +671,37 @@ inline int gen_grid(long long n) {
 namespace ab200 {
 // C++ entry points used by api.cu for the registered-operator mode (see driver.hpp)
 // halo planes of x for a row-partitioned operator: my first halo_lo entries go down, my last halo_hi go up
+// *xh: where the SpMV that follows must read its halo columns from (the communicator's own buffer has two parities)
 template <typename T>
-int exchange_halo(const CsrOpDesc<T>& op, const T* x) {
-  if (op.comm == 0 || (op.halo_lo == 0 && op.halo_hi == 0)) return 0;
+int exchange_halo_planes(int comm, int nloc, int halo_lo, int halo_hi, const T* x, T* halo, const T** xh) {
+  *xh = halo;
+  if (comm == 0 || (halo_lo == 0 && halo_hi == 0)) return 0;
   try {
-    NcclComm* c = comm_from_handle(op.comm);
+    NcclComm* c = comm_from_handle(comm);
     if (!c) return -1;
-    nccl_halo_exchange(c, x, op.halo, (size_t)op.halo_lo, x + (op.nrows - op.halo_hi), op.halo + op.halo_lo,
-                       (size_t)op.halo_hi, sizeof(T) == 8, cur_stream());
+    // my first plane goes down, my last plane goes up; halo = [plane from below | plane from above]
+    if (nccl_halo_is_peer_buffer(c, halo))
+      *xh = static_cast<const T*>(nccl_halo_exchange_peer(c, x, x + (nloc - halo_hi), cur_stream()));
+    else
+      nccl_halo_exchange(c, x, halo, (size_t)halo_lo, x + (nloc - halo_hi), halo + halo_lo, (size_t)halo_hi,
+                         sizeof(T) == 8, cur_stream());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "arpack_b200: halo exchange: %s\n", e.what());
     return -1;
   }
   return 0;
 }
+template <typename T>
+int exchange_halo(const CsrOpDesc<T>& op, const T* x, const T** xh) {
+  return exchange_halo_planes<T>(op.comm, op.nrows, op.halo_lo, op.halo_hi, x, op.halo, xh);
+}
 
 template <typename T>
 int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y) {
   if (op.comm != 0) {
-    if (exchange_halo(op, x) != 0) return -1;
-    return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, op.nrows, op.halo, op.nnz);
+    const T* xh = nullptr;
+    if (exchange_halo(op, x, &xh) != 0) return -1;
+    return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, op.nrows, xh, op.nnz);
   }
   return launch_spmv<T>(op.nrows, op.rowptr, op.col, op.val, x, y, 0, nullptr, op.nnz);
 }
@@ -705,9 +718,9 @@ int csr_op_apply_fused(const CsrOpDesc<T>& op, T inv, const StepGate<T>* gate, c
   // the row sums, halo entries included (every rank uses the same global norm); the epilogue dots would be local
   // partial sums there, so they are not produced
   const int nloc = op.comm != 0 ? op.nrows : 0;
-  const T* xh = op.comm != 0 ? op.halo : nullptr;
+  const T* xh = nullptr;
   if (op.comm != 0) {
-    if (exchange_halo(op, resid) != 0) return -1;
+    if (exchange_halo(op, resid, &xh) != 0) return -1;
     dots_out = nullptr;
   }
   const StepGate<T> g = gate ? *gate : StepGate<T>();
@@ -755,18 +768,9 @@ int ab200_csr_spmv_hostvec_f64(int nrows, int ncols, const int* rowptr, const in
 
 int ab200_csr_spmv_halo_f64(int comm, int nloc, int halo_lo, int halo_hi, const int* rowptr, const int* col,
                             const double* val, const double* x, double* y, double* halo_buf) {
-  try {
-    NcclComm* c = comm_from_handle(comm);
-    if (c && (halo_lo > 0 || halo_hi > 0)) {
-      // my first plane goes down, my last plane goes up; halo_buf = [plane from below | plane from above]
-      nccl_halo_exchange(c, x, halo_buf, (size_t)halo_lo, x + (nloc - halo_hi), halo_buf + halo_lo,
-                         (size_t)halo_hi, true, cur_stream());
-    }
-  } catch (const std::exception& e) {
-    std::fprintf(stderr, "arpack_b200: halo exchange: %s\n", e.what());
-    return -1;
-  }
-  return launch_spmv<double>(nloc, rowptr, col, val, x, y, nloc, halo_buf, nnz_of(nloc, rowptr));
+  const double* xh = halo_buf;
+  if (exchange_halo_planes<double>(comm, nloc, halo_lo, halo_hi, x, halo_buf, &xh) != 0) return -1;
+  return launch_spmv<double>(nloc, rowptr, col, val, x, y, nloc, xh, nnz_of(nloc, rowptr));
 }
 
 long long ab200_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* col, double* val) {

@@ -23,6 +23,11 @@ template <typename T>
 int csr_op_apply(const CsrOpDesc<T>& op, const T* x, T* y);
 // Fused K1+K2+K3: v_j = inv*resid, y = A v_j, dots_out = {v_j^T y, y^T y}; returns 1 when the operator's row
 // lengths do not suit the fused kernel (the caller then runs start_step + csr_op_apply)
+// whether csr_op_apply_fused would take the operator at all (short rows only)
+template <typename T>
+inline bool csr_op_fusable(const CsrOpDesc<T>& op) {
+  return op.nrows > 0 && (op.nnz > 0 ? (double)op.nnz / op.nrows : 8.0) <= 7.9;
+}
 // gate != nullptr: the scale is formed on the device from the previous step's mailbox slot (device-resident sweep),
 // and the kernel exits at once when the sweep's stop flag is set or the gate trips (see StepGate, vecops.hpp)
 template <typename T>

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "peer.cuh"
+
 namespace ab200 {
 namespace tma {
 
@@ -65,8 +67,12 @@ __device__ __forceinline__ T warp_sum(T v) {
 
 // Combine per-CTA partials deterministically: the CTA that takes the last ticket sums partial[b*pcols + c] over
 // b (lane-strided, then an xor tree) and writes out[c].  Must be reached by every thread of every CTA.
+// Multi-GPU (pub != nullptr && pub->nranks > 0): the rank's sums do not go to out[] but straight into every peer's
+// slot of the fused reduction *pub (peer.cuh) -- the all-reduce that used to follow this kernel as a launch of its
+// own starts here and ends in the prologue of the kernel that consumes the values.
 template <typename T>
-__device__ void finish_grid_reduce(T* partial, int pcols, int ncols, T* out, unsigned int* ticket) {
+__device__ void finish_grid_reduce(T* partial, int pcols, int ncols, T* out, unsigned int* ticket,
+                                   const PeerReduce* pub = nullptr) {
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
@@ -77,15 +83,20 @@ __device__ void finish_grid_reduce(T* partial, int pcols, int ncols, T* out, uns
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  const bool fused = pub != nullptr && pub->nranks > 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   for (int c = warp; c < ncols; c += nwarps) {
     T s = T(0);
     for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partial + (size_t)b * pcols + c);
     s = warp_sum(s);
-    if (lane == 0) out[c] = s;
+    if (lane == 0) {
+      if (fused) peer_put<T>(*pub, c, s);
+      else out[c] = s;
+    }
   }
   if (threadIdx.x == 0) *ticket = 0u;
+  if (fused) peer_publish(*pub);
 }
 
 // ---- host: tensor-map descriptors, cached (the encode call is a driver round trip of ~0.4 ms) ----

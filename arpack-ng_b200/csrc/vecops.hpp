@@ -15,6 +15,19 @@
 
 namespace ab200 {
 
+// One reduction across the ranks of a communicator that is FUSED into the kernels on both sides of it (multi-GPU,
+// peer memory over NVLink; comm_nccl.cpp, peer.cuh): the last CTA of the producing kernel stores this rank's partial
+// sums into every peer's slot and publishes `seq`; the consuming kernel waits for every rank's `seq` and adds the
+// slots in rank order (bit-identical on all ranks).  nranks == 0: not in use (single rank, or reduced by a separate
+// all-reduce).  Replaces MPI_ALLREDUCE of pdsaitr.f:604,720 / pdnorm2.f:72-80 without a launch of its own.
+struct PeerReduce {
+  unsigned char* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rank = 0, nranks = 0;
+  int kind = 0;                  // which slot family: 0 = [h, ||w||^2], 1 = [s, ||r||^2], 2 = [||r'||^2]
+  unsigned long long seq = 0;
+  long long timeout_cycles = 0;  // > 0: trap instead of waiting for ever (AB200_P2P_TIMEOUT_S)
+};
+
 // How a gated step kernel decides, on the device, whether and with which scale to run: the mailbox segments of
 // the step that precedes it (prev_j columns) hold ||w||^2 = A[prev_j], ||r||^2 = B[prev_j], ||r'||^2 = C[0] and
 // the DGKS flag C[1].  The kernel reproduces the host logic of IrlBase::finish_orth bit for bit:
@@ -30,6 +43,10 @@ struct StepGate {
   T tiny = 0;
   T* stop = nullptr;
   T stop_code = 0;
+  // multi-GPU: C[0] of the previous step is still spread over the ranks' peer slots; the gate waits for it, adds it up
+  // and leaves the sum in c_log[0] for the host (peer.nranks == 0: C[0] is already reduced)
+  PeerReduce peer;
+  T* c_log = nullptr;
 };
 
 template <typename T>

@@ -328,7 +328,7 @@ __global__ void k_start_step_gated(int64_t n, const StepGate<T> g, const T* __re
                                    T* __restrict__ outx, T* bx) {
   if (stopped(g.stop)) return;
   T inv;
-  if (!gate_eval(g, inv)) {
+  if (!gate_eval_block(g, inv)) {
     // every block takes the same decision from the same values; one thread records it.  No block of THIS kernel can
     // observe the store before its own entry check only if none is scheduled later -- which is why the check above
     // treats "already stopped" and "stops now" alike: nothing is written either way.
@@ -528,6 +528,7 @@ void CudaVecOps<T>::download2d(T* h, size_t ldd, const T* d, size_t lds, size_t 
 }
 template <typename T>
 void CudaVecOps<T>::sync() {
+  resolve_pending();
   AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 template <typename T>
@@ -557,7 +558,14 @@ T* CudaVecOps<T>::mailbox(size_t count) {
   return mb_dev_;
 }
 template <typename T>
+void CudaVecOps<T>::resolve_pending() {
+  if (!has_pending_) return;
+  has_pending_ = false;
+  nccl_peer_reduce_finalize(comm_, pending_, 1, pending_log_, pending_w2_, pending_r2_, sizeof(T) == 8, stream_);
+}
+template <typename T>
 void CudaVecOps<T>::fetch(T* host_dst, const T* mb, size_t count) {
+  resolve_pending();
   const size_t off = (size_t)(mb - mb_dev_);
   AB200_CUDA_CHECK(cudaMemcpyAsync(mb_pinned_ + off, mb, sizeof(T) * count, cudaMemcpyDeviceToHost, stream_));
   AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -566,6 +574,7 @@ void CudaVecOps<T>::fetch(T* host_dst, const T* mb, size_t count) {
 }
 template <typename T>
 void CudaVecOps<T>::post(T* mb, const T* host_src, size_t count) {
+  resolve_pending();
   const size_t off = (size_t)(mb - mb_dev_);
   AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
   std::memcpy(mb_pinned_ + off, host_src, sizeof(T) * count);
@@ -574,6 +583,7 @@ void CudaVecOps<T>::post(T* mb, const T* host_src, size_t count) {
 template <typename T>
 void CudaVecOps<T>::allreduce_sum(T* mb, size_t count) {
   if (comm_ == nullptr || count == 0) return;
+  resolve_pending();
   nccl_allreduce_sum(comm_, mb, count, sizeof(T) == 8, stream_);
   launch_stats().allreduces++;
 }
@@ -689,13 +699,16 @@ void CudaVecOps<T>::larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) {
 
 template <typename T>
 void CudaVecOps<T>::start_step(int64_t n, T inv, const T* resid, T* vj, T* outx, T* bx, bool from_resid) {
+  resolve_pending();
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? (from_resid ? 4.0 : 5.0) : 3.0));
   k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid, stop_);
   AB200_LAUNCHED();
 }
 template <typename T>
-void CudaVecOps<T>::start_step_gated(int64_t n, const StepGate<T>& g, const T* resid, T* vj, T* outx, T* bx) {
+void CudaVecOps<T>::start_step_gated(int64_t n, const StepGate<T>& g0, const T* resid, T* vj, T* outx, T* bx) {
+  StepGate<T> g = g0;
+  attach_pending(g);  // multi-GPU: the gate finishes the reduction of ||r'||^2 itself
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? 4.0 : 3.0));
   k_start_step_gated<T><<<grid, 256, 0, stream_>>>(n, g, resid, vj, outx, bx);
@@ -742,18 +755,21 @@ void CudaVecOps<T>::update_generic(int64_t n, int j, const T* v, int64_t ldv, co
 
 template <typename T>
 void CudaVecOps<T>::dots(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* out) {
+  resolve_pending();
   if (kernel_mode_ == 0 && fast_path_ok(n, j, v, ldv) && dots_tma(n, j, v, ldv, x, y, out)) return;
   dots_generic(n, j, v, ldv, x, y, out);
 }
 template <typename T>
 void CudaVecOps<T>::update(int64_t n, int j, const T* v, int64_t ldv, const T* coef, const T* src, T* dst,
                            T* nrm2) {
+  resolve_pending();
   update_generic(n, j, v, ldv, coef, src, dst, nrm2, nullptr, nullptr, nullptr);
 }
 
 template <typename T>
 void CudaVecOps<T>::orth_step(int64_t n, int j, const T* v, int64_t ldv, const T* w, T* resid, T* mbA, T* mbB,
                               T* mbC) {
+  resolve_pending();
   if (kernel_mode_ == 0 && fast_path_ok(n, j, v, ldv) && orth_step_tma(n, j, v, ldv, w, resid, mbA, mbB, mbC))
     return;
   // generic composition: 4 sweeps over V_j (the reference's own dependency order, K6 K7 K9 K9)

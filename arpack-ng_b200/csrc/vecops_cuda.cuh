@@ -28,6 +28,10 @@ struct NcclComm;
 void nccl_allreduce_sum(NcclComm* c, void* buf, size_t count, bool is_double, cudaStream_t s);
 int nccl_rank(const NcclComm* c);
 int nccl_nranks(const NcclComm* c);
+// reductions fused into the kernels on both sides (peer memory; comm_nccl.cpp, peer.cuh)
+bool nccl_peer_reduce_begin(NcclComm* c, int kind, PeerReduce* out);
+void nccl_peer_reduce_finalize(NcclComm* c, const PeerReduce& pr, int count, void* log, const void* pred_w2,
+                               const void* pred_r2, bool is_double, cudaStream_t s);
 
 // process-wide launch statistics (bench.py reports gpu_launches from here)
 struct LaunchStats {
@@ -134,6 +138,19 @@ class CudaVecOps final : public VecOps<T> {
   }
   unsigned int* reduction_ticket() { return ticket_; }
   const T* stop_flag() const { return stop_; }
+  // Multi-GPU: the norm ||r'||^2 of the last orth_step may still sit in the ranks' peer slots (its reduction is fused
+  // into whichever kernel consumes it).  A gated consumer takes it over with attach_pending(); every other use of the
+  // mailbox goes through resolve_pending(), which finishes the reduction with one small kernel.
+  void attach_pending(StepGate<T>& g) {
+    if (has_pending_ && g.C == pending_log_) {
+      g.peer = pending_;
+      g.c_log = pending_log_;
+      has_pending_ = false;
+    } else {
+      resolve_pending();
+    }
+  }
+  void resolve_pending();
 
  private:
   cudaStream_t stream_;
@@ -146,6 +163,12 @@ class CudaVecOps final : public VecOps<T> {
   T* mb_pinned_ = nullptr;
   // sticky stop flag of a device-resident sweep (mailbox entry, 0 = run); checked by every step kernel
   T* stop_ = nullptr;
+  // fused reduction of ||r'||^2 that no kernel has consumed yet (see attach_pending)
+  bool has_pending_ = false;
+  PeerReduce pending_;
+  T* pending_log_ = nullptr;
+  const T* pending_w2_ = nullptr;
+  const T* pending_r2_ = nullptr;
   // two-stage reduction scratch: partial_[grid][pcols_] and a ticket counter
   T* partial_ = nullptr;
   size_t partial_count_ = 0;

@@ -60,26 +60,55 @@ struct OrthParams {
   const T* pred_r2;
   T* flag_out;
   const T* stop;  // sticky stop flag of a device-resident sweep (may be null)
+  // multi-GPU: reductions fused into the kernels (peer.cuh).  pub: this kernel's sums go to the peers' slots instead
+  // of `out`; sub: the coefficients (and the value behind them) come from the peers' slots instead of `coef` /
+  // `pred_r2`, and CTA 0 leaves the reduced values in sub_log for the host.  nranks == 0: not in use.
+  PeerReduce pub, sub;
+  T* sub_log;
 };
+
+// Consumer side of a fused reduction: wait for every rank, add the slots in rank order into cs[0..j) (zero-padded up
+// to MAXB*CB) and return value j; CTA 0 leaves all j+1 sums in p.sub_log.  Called by ALL threads of the CTA, before any
+// early exit that depends on the values.
+template <typename T>
+__device__ __forceinline__ T fused_coefs(const OrthParams<T>& p, T* cs) {
+  __shared__ T s_tail;
+  peer_wait_all(p.sub);
+  for (int k = threadIdx.x; k < MAXB * CB + 1; k += blockDim.x) {
+    if (k <= p.j) {
+      const T v = peer_sum<T>(p.sub, k);
+      if (k < p.j) cs[k] = v;
+      else s_tail = v;
+      if (blockIdx.x == 0 && p.sub_log != nullptr) p.sub_log[k] = v;
+    } else {
+      cs[k - 1] = T(0);
+    }
+  }
+  __syncthreads();
+  return s_tail;
+}
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreadsTma, 1)
 k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   if (stopped(p.stop)) return;
-  if (MODE == UPD && p.pred_w2 != nullptr) {
-    // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
-    const T wn = sqrt(*p.pred_w2), rn = sqrt(*p.pred_r2);
-    if (rn > T(0.717f) * wn) {
-      if (blockIdx.x == 0 && threadIdx.x == 0 && p.flag_out) *p.flag_out = T(0);
-      return;
-    }
-  }
   T* tiles = reinterpret_cast<T*>(smem);
   unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
   T* ps = reinterpret_cast<T*>(aux);                     // [NG groups][2 buffers][2 halves][R]
   T* cs = ps + NG * 4 * R;                               // [MAXB*CB] coefficients
   T* gsum = cs + MAXB * CB;                              // [MAXB*CB + 8] partials of consumer group 1
+  const bool sub = MODE != DOTS && p.sub.nranks > 0;
+  T tail = T(0);
+  if (sub) tail = fused_coefs(p, cs);
+  if (MODE == UPD && p.pred_w2 != nullptr) {
+    // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
+    const T wn = sqrt(*p.pred_w2), rn = sqrt(sub ? tail : *p.pred_r2);
+    if (rn > T(0.717f) * wn) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.flag_out) *p.flag_out = T(0);
+      return;
+    }
+  }
   uint64_t* full = reinterpret_cast<uint64_t*>(gsum + MAXB * CB + 8);
   uint64_t* empty = full + MAXST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -90,7 +119,7 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     }
     mbar_fence_init();
   }
-  if (MODE != DOTS)
+  if (MODE != DOTS && !sub)
     for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
   __syncthreads();
 
@@ -239,7 +268,7 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
   }
   if (p.out == nullptr) return;
   if (MODE == UPD && blockIdx.x == 0 && tid == 0 && p.flag_out) *p.flag_out = T(1);
-  finish_grid_reduce(p.partial, p.pcols, (MODE == UPD) ? 1 : p.j + 1, p.out, p.ticket);
+  finish_grid_reduce(p.partial, p.pcols, (MODE == UPD) ? 1 : p.j + 1, p.out, p.ticket, &p.pub);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,18 +283,21 @@ __global__ void __launch_bounds__(kThreadsTma, 1)
 k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   if (stopped(p.stop)) return;
+  T* tiles = reinterpret_cast<T*>(smem);
+  unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
+  T* wsum = reinterpret_cast<T*>(aux);                   // [NG*NCW warps][MAXB*CB columns]  (== NG*4*R elements)
+  T* cs = wsum + NG * 4 * R;                             // [MAXB*CB] coefficients
+  const bool sub = p.sub.nranks > 0;
+  T tail = T(0);
+  if (sub) tail = fused_coefs(p, cs);
   if (!SPEC && p.pred_w2 != nullptr) {
     // the reference's DGKS test (dsaitr.f:656), evaluated identically by every thread
-    const T wn = sqrt(*p.pred_w2), rn = sqrt(*p.pred_r2);
+    const T wn = sqrt(*p.pred_w2), rn = sqrt(sub ? tail : *p.pred_r2);
     if (rn > T(0.717f) * wn) {
       if (blockIdx.x == 0 && threadIdx.x == 0 && p.flag_out) *p.flag_out = T(0);
       return;
     }
   }
-  T* tiles = reinterpret_cast<T*>(smem);
-  unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
-  T* wsum = reinterpret_cast<T*>(aux);                   // [NG*NCW warps][MAXB*CB columns]  (== NG*4*R elements)
-  T* cs = wsum + NG * 4 * R;                             // [MAXB*CB] coefficients
   T* wnrm = cs + MAXB * CB;                              // [NG*NCW] per-warp ||r||^2
   uint64_t* full = reinterpret_cast<uint64_t*>(wnrm + MAXB * CB + 8);
   uint64_t* empty = full + MAXST;
@@ -277,7 +309,8 @@ k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
     }
     mbar_fence_init();
   }
-  for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
+  if (!sub)
+    for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
   __syncthreads();
 
   const int64_t ntiles = (p.n + R - 1) / R;
@@ -398,7 +431,7 @@ k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
   }
   if (p.out == nullptr) return;
   if (!SPEC && blockIdx.x == 0 && tid == 0 && p.flag_out) *p.flag_out = T(1);
-  finish_grid_reduce(p.partial, p.pcols, SPEC ? p.j + 1 : 1, p.out, p.ticket);
+  finish_grid_reduce(p.partial, p.pcols, SPEC ? p.j + 1 : 1, p.out, p.ticket, &p.pub);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -687,6 +720,12 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
                                   T* mbC) {
   const int grid = (int)std::min<int64_t>((n + R - 1) / R, num_sms_);
   ensure_partial((size_t)grid * (j + 1));
+  // multi-GPU with peer memory: the three reductions of the step are fused into the kernels -- the last CTA of the
+  // producer stores this rank's sums into every peer's slot, the consumer's prologue adds the slots in rank order
+  // (peer.cuh).  Otherwise a separate all-reduce (one small kernel, or ncclAllReduce) follows each sweep.
+  PeerReduce prA, prB, prC;
+  const bool fuse = comm_ != nullptr && j + 1 <= kPeerMaxCount && nccl_peer_reduce_begin(comm_, 0, &prA) &&
+                    nccl_peer_reduce_begin(comm_, 1, &prB) && nccl_peer_reduce_begin(comm_, 2, &prC);
   // sweep A: h = V^T w, ||w||^2
   {
     OrthParams<T> p{};
@@ -694,10 +733,13 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
     p.x = w; p.y = w; p.partial = partial_; p.out = mbA; p.ticket = ticket_; p.stop = stop_;
-    if (!launch_orth<T, DOTS>(stream_, num_sms_, v, ldv, p, "dots_tma", (double)sizeof(T) * n * (j + 1.0)))
+    if (fuse) p.pub = prA;
+    if (!launch_orth<T, DOTS>(stream_, num_sms_, v, ldv, p, "dots_tma", (double)sizeof(T) * n * (j + 1.0))) {
+      if (fuse) throw CudaError("dots_tma launch failed with a fused reduction in flight");
       return false;
+    }
   }
-  allreduce_sum(mbA, (size_t)j + 1);
+  if (!fuse) allreduce_sum(mbA, (size_t)j + 1);
   // sweep B: r = w - V h, ||r||^2, s = V^T r (speculative)
   {
     OrthParams<T> p{};
@@ -705,10 +747,11 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     geometry<T>(j, aligned16(w), p);
     p.pcols = j + 1;
     p.x = w; p.dst = resid; p.coef = mbA; p.partial = partial_; p.out = mbB; p.ticket = ticket_; p.stop = stop_;
+    if (fuse) { p.sub = prA; p.sub_log = mbA; p.pub = prB; }
     if (!launch_upd<T, true>(stream_, num_sms_, v, ldv, p, "update_spec_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("update_spec_tma launch failed after dots_tma succeeded");
   }
-  allreduce_sum(mbB, (size_t)j + 1);
+  if (!fuse) allreduce_sum(mbB, (size_t)j + 1);
   // sweep C (only if the DGKS test fires, decided on the device): r -= V s, ||r||^2
   {
     OrthParams<T> p{};
@@ -717,10 +760,21 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     p.pcols = 1;
     p.x = resid; p.dst = resid; p.coef = mbB; p.partial = partial_; p.out = mbC; p.ticket = ticket_;
     p.pred_w2 = mbA + j; p.pred_r2 = mbB + j; p.flag_out = mbC + 1; p.stop = stop_;
+    if (fuse) { p.sub = prB; p.sub_log = mbB; p.pub = prC; }
     if (!launch_upd<T, false>(stream_, num_sms_, v, ldv, p, "reorth_tma", (double)sizeof(T) * n * (j + 2.0)))
       throw CudaError("reorth_tma launch failed after dots_tma succeeded");
   }
-  allreduce_sum(mbC, 1);
+  if (fuse) {
+    // ||r'||^2 stays in the peer slots until somebody needs it: the gated start of the next step (attach_pending)
+    // or, failing that, a one-block finalize kernel in front of the next mailbox read (resolve_pending)
+    has_pending_ = true;
+    pending_ = prC;
+    pending_log_ = mbC;
+    pending_w2_ = mbA + j;
+    pending_r2_ = mbB + j;
+  } else {
+    allreduce_sum(mbC, 1);
+  }
   return true;
 }
 

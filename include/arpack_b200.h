@@ -253,6 +253,12 @@ int ab200_comm_rank(int handle);
  * per all-reduce, sums in rank order), 0 when they use ncclAllReduce (IPC unavailable, > 8 ranks, AB200_P2P=0) */
 int ab200_comm_uses_p2p(int handle);
 int ab200_comm_size(int handle);
+/* Collective: the communicator's own halo receive buffer for a row-partitioned operator whose lower / upper neighbour
+ * planes hold halo_lo / halo_hi elements of elem_size bytes (8 or 4).  Passed as halo_buf to ab200_csr_spmv_halo_f64 /
+ * ab200_register_csr_halo_op_f64 it makes the plane exchange of PARPACK/EXAMPLES/MPI/pdsdrv1.f:463-483 run through peer
+ * memory (the neighbours store their planes into it over NVLink).  NULL: peer memory is unavailable -- allocate an
+ * ordinary device buffer of halo_lo + halo_hi elements instead (exchange by ncclSend/ncclRecv). */
+void* ab200_comm_halo_buffer(int handle, long long halo_lo, long long halo_hi, int elem_size);
 
 /* ---- driver layer: the user's OP for the arpackmm-style tool (EXAMPLES/MATRIX_MARKET/arpackSolver.hpp:806-841
  * does these products with Eigen on the CPU).  All pointers are DEVICE pointers unless named *_host. ---- */
