@@ -139,6 +139,14 @@ def lib():
     L.ab200_gen_convdiff2d.argtypes = [C.c_int, C.c_double, vp, vp, vp]
     L.ab200_gen_convdiff2d.restype = C.c_longlong
     L.ab200_fill_hash_f64.argtypes = [C.c_longlong, C.c_longlong, C.c_ulonglong, vp]
+    L.ab200_gen_randsparse.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_ulonglong, vp, vp, vp]
+    L.ab200_gen_randsparse.restype = C.c_longlong
+    L.ab200_csr_transpose_f64.argtypes = [C.c_int, C.c_int, C.c_longlong, vp, vp, vp, vp, vp, vp]
+    L.ab200_gram_create.argtypes = [C.c_int, C.c_int]
+    L.ab200_gram_add_shard.argtypes = [C.c_int, C.c_int, C.c_longlong, vp, vp, vp, vp, vp, vp]
+    L.ab200_gram_apply.argtypes = [C.c_int, vp, vp]
+    L.ab200_gram_destroy.argtypes = [C.c_int]
+    L.ab200_register_gram_op_f64.argtypes = [vp, C.c_int]
     L.ab200_residuals_f64.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.c_longlong, vp, vp]
     _lib = L
     return L
@@ -314,7 +322,13 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
         if resid is not None:
             res.copy_(torch.as_tensor(resid, dtype=t_dt))
             info[0] = 1
-    if registered_op is not None:
+    if isinstance(registered_op, GramOperator):
+        # opt-in extension: the library applies the A^T A operator itself (one *aupd call per solve)
+        if L.ab200_register_gram_op_f64(workl.ctypes.data, registered_op.h) != 0:
+            raise ArpackB200Error("register_gram_op failed")
+        if op is None:
+            op = registered_op
+    elif registered_op is not None:
         # opt-in extension: the library applies the CSR operator itself (one *aupd call per solve)
         if registered_op.val.dtype not in (t_dt, np_dt):
             raise ArpackB200Error("registered_op values must have the solve's dtype")
@@ -352,7 +366,7 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
     # operators that accept raw addresses (CsrOperator on device arrays) skip the per-step tensor views
     fast = getattr(op, "apply_ptr", None) if (not host_buffers and not (mode >= 3 and bmat == "G")) else None
     if fast is not None and comm is not None:
-        fast = op.apply_halo_ptr if hasattr(op, "halo_lo") else None
+        fast = getattr(op, "apply_comm_ptr", None) or (op.apply_halo_ptr if hasattr(op, "halo_lo") else None)
     wbase, isz = _addr(workd), np_dt.itemsize
     nsteps = 0
     while True:
@@ -382,7 +396,9 @@ def solve(op, n, nev, ncv, which, *, sym=True, tol=0.0, mxiter=300, bmat="I", mo
             break
     out = Result(info=int(info[0]), iparam=iparam.copy(), ipntr=ipntr.copy(), workl=workl.copy(), v=v, resid=res,
                  nconv=int(iparam[4]), nsteps=nsteps, workd=workd,
-                 fused_dot_maxdiff=(L.ab200_fused_dot_maxdiff(workl.ctypes.data) if registered_op is not None else None))
+                 fused_dot_maxdiff=(L.ab200_fused_dot_maxdiff(workl.ctypes.data)
+                                    if registered_op is not None and not isinstance(registered_op, GramOperator)
+                                    else None))
     if info[0] < 0 or not eupd:
         L.ab200_release(workl.ctypes.data)   # no *eupd will follow: drop the solve's context (and its HBM mirrors)
         return out
@@ -702,3 +718,115 @@ def slab_partition(nlines, world, rank):
     cnt = base + (1 if rank < rem else 0)
     first = rank * base + min(rank, rem)
     return first, cnt
+
+
+# ---- OP = A^T A on a row-sharded sparse A (BASELINE config 5: SVD through dsaupd, EXAMPLES/SVD/dsvd.f) ---------------
+def randsparse_numpy(row0, nrows, ncols, per_row=16, seed=0x5EED):
+    """CPU twin of ab200_gen_randsparse (same bits): rows [row0, row0+nrows) of the synthetic matrix of SURVEY.md 8d as a
+    scipy CSR matrix (duplicate columns of a row are summed, exactly as the product does)."""
+    import scipy.sparse as sp
+
+    def mix(x):
+        with np.errstate(over="ignore"):
+            x = x + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return x ^ (x >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        r = np.repeat(np.arange(row0, row0 + nrows, dtype=np.uint64), per_row)
+        k = np.tile(np.arange(per_row, dtype=np.uint64), nrows)
+        h1 = mix(np.uint64(seed) + np.uint64(per_row) * r + k)
+    h2 = mix(h1)
+    col = (h1 % np.uint64(ncols)).astype(np.int64)
+    val = 2.0 * ((h2 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)) - 1.0
+    rows = (r - np.uint64(row0)).astype(np.int64)
+    return sp.csr_matrix((val, (rows, col)), shape=(nrows, ncols))
+
+
+class GramOperator:
+    """z = A^T A x for a row-sharded sparse A resident in HBM (gram.cu): the caller's `av` + `atv` of
+    EXAMPLES/SVD/dsvd.f:342-343.  comm = None: one process, vectors of ncols entries.  comm = handle: this rank owns
+    `shards` row blocks of A and the slice [rank*ncols/world, ...) of the eigenproblem vectors (PARPACK's layout)."""
+
+    def __init__(self, ncols, comm=None):
+        self.ncols, self.comm = int(ncols), comm
+        self.h = lib().ab200_gram_create(comm or 0, self.ncols)
+        if self.h < 1:
+            raise ArpackB200Error(f"ab200_gram_create failed ({self.h}): ncols must be a multiple of the rank count")
+        self._keep = []   # the shards' device arrays stay alive as long as the operator
+        self.nnz = 0
+        self.rows = 0
+        world = lib().ab200_comm_size(comm) if comm else 1
+        self.n = self.ncols // world     # local length of the eigenproblem vectors
+
+    def add_shard(self, row0, nrows, per_row=16, seed=0x5EED, device="cuda"):
+        """Generate rows [row0, row0+nrows) of the synthetic matrix on the device, build the shard's transpose."""
+        import torch
+        L = lib()
+        nnz = L.ab200_gen_randsparse(row0, nrows, self.ncols, per_row, seed, None, None, None)
+        if nnz < 0:
+            raise ArpackB200Error("randsparse: shard too large for int32 indices")
+        i32, f64 = torch.int32, torch.float64
+        rp, col, val = (torch.empty(nrows + 1, dtype=i32, device=device), torch.empty(nnz, dtype=i32, device=device),
+                        torch.empty(nnz, dtype=f64, device=device))
+        if L.ab200_gen_randsparse(row0, nrows, self.ncols, per_row, seed, rp.data_ptr(), col.data_ptr(),
+                                  val.data_ptr()) != nnz:
+            raise ArpackB200Error("randsparse generator failed")
+        return self.add_csr(nrows, rp, col, val)
+
+    def add_csr(self, nrows, rp, col, val):
+        import torch
+        L = lib()
+        nnz = int(val.numel())
+        trp = torch.empty(self.ncols + 1, dtype=torch.int32, device=val.device)
+        tcol = torch.empty(nnz, dtype=torch.int32, device=val.device)
+        tval = torch.empty(nnz, dtype=torch.float64, device=val.device)
+        if L.ab200_csr_transpose_f64(nrows, self.ncols, nnz, rp.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                     trp.data_ptr(), tcol.data_ptr(), tval.data_ptr()) != 0:
+            raise ArpackB200Error("csr transpose failed")
+        if L.ab200_gram_add_shard(self.h, nrows, nnz, rp.data_ptr(), col.data_ptr(), val.data_ptr(), trp.data_ptr(),
+                                  tcol.data_ptr(), tval.data_ptr()) != 0:
+            raise ArpackB200Error("gram_add_shard failed")
+        self._keep.append((rp, col, val, trp, tcol, tval))
+        self.nnz += nnz
+        self.rows += nrows
+        return self
+
+    @staticmethod
+    def randsparse(nrows_total, ncols, per_row=16, seed=0x5EED, comm=None, shard_rows=None, device="cuda"):
+        """The config-5 operator: A is nrows_total x ncols; under a communicator this rank takes its block of rows
+        (slab_partition), which is further cut into shards of at most shard_rows rows (default: so that a shard's
+        product vector is 20 MB, comfortably L2-resident next to x)."""
+        L = lib()
+        world = L.ab200_comm_size(comm) if comm else 1
+        rank = L.ab200_comm_rank(comm) if comm else 0
+        first, cnt = slab_partition(nrows_total, world, rank)
+        shard_rows = shard_rows or 2_500_000
+        G = GramOperator(ncols, comm)
+        r = first
+        while r < first + cnt:
+            m = min(shard_rows, first + cnt - r)
+            G.add_shard(r, m, per_row, seed, device)
+            r += m
+        return G
+
+    def apply_ptr(self, xptr, yptr):
+        if lib().ab200_gram_apply(self.h, xptr, yptr) != 0:
+            raise ArpackB200Error("gram_apply failed")
+
+    def apply_comm_ptr(self, comm, xptr, yptr):
+        self.apply_ptr(xptr, yptr)
+
+    def __call__(self, x, y, *_):
+        self.apply_ptr(x.data_ptr(), y.data_ptr())
+
+    def spmv_bytes(self):
+        """Algorithmic traffic of one OP: both CSR copies streamed once, x and the shard products gathered once."""
+        return 2 * self.nnz * 12 + (self.rows + len(self._keep) * (self.ncols + 2)) * 4 + \
+            (self.ncols * 8 * 3 + self.rows * 16) * 1
+
+    def close(self):
+        if self.h:
+            lib().ab200_gram_destroy(self.h)
+            self.h = 0
+            self._keep = []

@@ -31,6 +31,7 @@
 
 namespace ab200 {
 NcclComm* comm_from_handle(int handle);
+int gram_apply(int handle, const double* x_loc, double* z_loc);  // gram.cu
 // complex entry points live in api_cplx.cu
 void release_cplx(const void* workl);
 void release_all_cplx();
@@ -204,6 +205,31 @@ void attach_registered_op(Ctx<T>* c, Solver* solver, const void* key, int n) {
       });
 }
 
+// A^T A operators (gram.cu) registered for the solve keyed to a workl address: handle from ab200_gram_create()
+std::unordered_map<const void*, int>& registered_grams() {
+  static std::unordered_map<const void*, int> t;
+  return t;
+}
+template <typename T, typename Solver>
+bool attach_gram_op(Solver* solver, const void* key) {
+  int h = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = registered_grams().find(key);
+    if (it == registered_grams().end()) return false;
+    h = it->second;
+    registered_grams().erase(it);  // one-shot, like the CSR registration
+  }
+  if (sizeof(T) != 8) throw CudaError("registered A^T A operator: FP64 only");
+  solver->set_registered_op(
+      [h](const T* x, T* y) {
+        if (gram_apply(h, reinterpret_cast<const double*>(x), reinterpret_cast<double*>(y)) != 0)
+          throw CudaError("registered A^T A operator: product failed");
+      },
+      nullptr);
+  return true;
+}
+
 template <typename T>
 Ctx<T>* find_ctx(const void* key) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -231,11 +257,15 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
       if (SYM) c->sym = std::make_unique<IrlSym<T>>(c->ops.get(), par, seed);
       else c->nonsym = std::make_unique<IrlNonsym<T>>(c->ops.get(), par, seed, &Globals<T>::smlnum_first);
       if (iparam[6] == 1 && bmat[0] == 'I') {
-        if (SYM) attach_registered_op<T>(c, c->sym.get(), workl, n);
-        else attach_registered_op<T>(c, c->nonsym.get(), workl, n);
+        const bool gram = SYM ? attach_gram_op<T>(c->sym.get(), workl) : attach_gram_op<T>(c->nonsym.get(), workl);
+        if (!gram) {
+          if (SYM) attach_registered_op<T>(c, c->sym.get(), workl, n);
+          else attach_registered_op<T>(c, c->nonsym.get(), workl, n);
+        }
       } else {
         std::lock_guard<std::mutex> lk(g_mu);
         registered_ops<T>().erase(workl);  // not applicable to this solve (bmat='G', modes 2-5)
+        registered_grams().erase(workl);
       }
       // device-resident sweeps (no host round trip per step) need hand-off slots the device reaches by itself: a
       // device-resident workd, or a registered operator (then no hand-off happens at all)
@@ -561,12 +591,24 @@ void ab200_release(const void* workl) {
   table<float>().erase(workl);
   registered_ops<double>().erase(workl);
   registered_ops<float>().erase(workl);
+  registered_grams().erase(workl);
 }
 void ab200_release_all(void) {
   release_all_cplx();
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().clear();
   table<float>().clear();
+  registered_ops<double>().clear();  // descriptors hold the caller's pointers: none may outlive this call
+  registered_ops<float>().clear();
+  registered_grams().clear();
+}
+// the same registration for an A^T A operator built with ab200_gram_create()/ab200_gram_add_shard() (gram.cu): the
+// library applies it inside dsaupd_c / pdsaupd_c, one call runs the whole solve
+int ab200_register_gram_op_f64(const void* workl, int gram_handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (gram_handle <= 0) { registered_grams().erase(workl); return 0; }
+  registered_grams()[workl] = gram_handle;
+  return 0;
 }
 void ab200_launch_stats(unsigned long long* out4) {
   const LaunchStats& s = launch_stats();

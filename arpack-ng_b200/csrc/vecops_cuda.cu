@@ -558,6 +558,26 @@ T* CudaVecOps<T>::mailbox(size_t count) {
   return mb_dev_;
 }
 template <typename T>
+bool CudaVecOps<T>::ranks_agree_on_fusing(int64_t n, int j, const T* v, int64_t ldv) {
+  if (comm_ == nullptr) return false;
+  if (agreed_v_ == (const void*)v && agreed_ldv_ == ldv) return agreed_fuse_;
+  // one tiny all-reduce + host read per solve: does EVERY rank take the TMA-tiled path for this V?
+  const T mine = (kernel_mode_ == 0 && fast_path_ok(n, j, v, ldv)) ? T(1) : T(0);
+  T* slot = partial_;  // reduction scratch: free between kernels
+  ensure_partial(8);
+  slot = partial_;
+  AB200_CUDA_CHECK(cudaMemcpyAsync(slot, &mine, sizeof(T), cudaMemcpyHostToDevice, stream_));
+  AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  nccl_allreduce_sum(comm_, slot, 1, sizeof(T) == 8, stream_);
+  T sum = T(0);
+  AB200_CUDA_CHECK(cudaMemcpyAsync(&sum, slot, sizeof(T), cudaMemcpyDeviceToHost, stream_));
+  AB200_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  agreed_v_ = v;
+  agreed_ldv_ = ldv;
+  agreed_fuse_ = (sum == T(nccl_nranks(comm_)));
+  return agreed_fuse_;
+}
+template <typename T>
 void CudaVecOps<T>::resolve_pending() {
   if (!has_pending_) return;
   has_pending_ = false;
@@ -770,6 +790,7 @@ template <typename T>
 void CudaVecOps<T>::orth_step(int64_t n, int j, const T* v, int64_t ldv, const T* w, T* resid, T* mbA, T* mbB,
                               T* mbC) {
   resolve_pending();
+  if (comm_ != nullptr) ranks_agree_on_fusing(n, j, v, ldv);  // collective, once per solve
   if (kernel_mode_ == 0 && fast_path_ok(n, j, v, ldv) && orth_step_tma(n, j, v, ldv, w, resid, mbA, mbB, mbC))
     return;
   // generic composition: 4 sweeps over V_j (the reference's own dependency order, K6 K7 K9 K9)

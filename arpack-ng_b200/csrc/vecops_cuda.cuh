@@ -169,6 +169,12 @@ class CudaVecOps final : public VecOps<T> {
   T* pending_log_ = nullptr;
   const T* pending_w2_ = nullptr;
   const T* pending_r2_ = nullptr;
+  // Fused reductions are a protocol between the ranks' kernels: either every rank runs the TMA-tiled kernels for this
+  // solve's V (alignment, leading dimension -- rank-local properties) or nobody fuses.  Agreed once per (V, ldv).
+  const void* agreed_v_ = nullptr;
+  int64_t agreed_ldv_ = -1;
+  bool agreed_fuse_ = false;
+  bool ranks_agree_on_fusing(int64_t n, int j, const T* v, int64_t ldv);
   // two-stage reduction scratch: partial_[grid][pcols_] and a ticket counter
   T* partial_ = nullptr;
   size_t partial_count_ = 0;

@@ -724,7 +724,8 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
   // producer stores this rank's sums into every peer's slot, the consumer's prologue adds the slots in rank order
   // (peer.cuh).  Otherwise a separate all-reduce (one small kernel, or ncclAllReduce) follows each sweep.
   PeerReduce prA, prB, prC;
-  const bool fuse = comm_ != nullptr && j + 1 <= kPeerMaxCount && nccl_peer_reduce_begin(comm_, 0, &prA) &&
+  const bool fuse = comm_ != nullptr && j + 1 <= kPeerMaxCount && agreed_fuse_ &&
+                    nccl_peer_reduce_begin(comm_, 0, &prA) &&
                     nccl_peer_reduce_begin(comm_, 1, &prB) && nccl_peer_reduce_begin(comm_, 2, &prC);
   // sweep A: h = V^T w, ||w||^2
   {

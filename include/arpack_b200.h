@@ -282,6 +282,26 @@ long long ab200_gen_laplace2d(int nx, int ny, double scale, int* rowptr, int* co
 long long ab200_gen_laplace3d(int nx, int ny, int nz, int z0, int nzloc, double diag, int* rowptr, int* col,
                               double* val);
 long long ab200_gen_convdiff2d(int nx, double rho, int* rowptr, int* col, double* val);
+/* ---- OP = A^T A on a row-sharded sparse A (BASELINE config 5; the caller's av + atv of EXAMPLES/SVD/dsvd.f:342-343,
+ * 400-470, singular values = sqrt of the Ritz values, :416) ---- */
+/* rows [row0, row0 + nrows) of the synthetic matrix of SURVEY.md 8d: exactly per_row entries per row, entry k of row r at
+ * column splitmix64(seed + per_row*r + k) mod ncols with value 2u-1, u = top 53 bits of splitmix64(that hash) / 2^53.
+ * rowptr = NULL queries nnz. */
+long long ab200_gen_randsparse(long long row0, int nrows, int ncols, int per_row, unsigned long long seed, int* rowptr,
+                               int* col, double* val);
+/* CSR of A^T (ncols x nrows) from the CSR of A, on the device; entries of a row of A^T in ascending row order of A */
+int ab200_csr_transpose_f64(int nrows, int ncols, long long nnz, const int* rowptr, const int* col, const double* val,
+                            int* t_rowptr, int* t_col, double* t_val);
+/* handle of an operator z = sum_s A_s^T (A_s x) over the shards added below; comm = 0: one process, x and z hold ncols
+ * entries; comm = handle of ab200_comm_create(): x and z are this rank's slice of ncols / nranks entries (all-gather of
+ * x, local products, reduce-scatter of the partial sums).  Device arrays stay owned by the caller. */
+int ab200_gram_create(int comm, int ncols);
+int ab200_gram_add_shard(int handle, int nrows, long long nnz, const int* rowptr, const int* col, const double* val,
+                         const int* t_rowptr, const int* t_col, const double* t_val);
+int ab200_gram_apply(int handle, const double* x_loc, double* z_loc);
+void ab200_gram_destroy(int handle);
+/* let dsaupd_c / pdsaupd_c apply the operator themselves for the solve keyed to workl (one call runs the whole solve) */
+int ab200_register_gram_op_f64(const void* workl, int gram_handle);
 /* start vector of SURVEY.md §8(d): resid[i] = 2 u(i0+i) - 1, u = top 53 bits of splitmix64(seed + i) / 2^53 */
 int ab200_fill_hash_f64(long long n, long long i0, unsigned long long seed, double* x);
 /* residual check of arpackSolver.hpp:297-352: out[k] = || A z_k - d_k z_k ||_2 (device z, host d/out) */

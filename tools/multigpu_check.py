@@ -11,6 +11,8 @@ the same eigenvalues to 1e-10 relative (the bar of BASELINE.json's north_star).
   3. the same solve with the operator registered (ab200_register_csr_halo_op_f64): no hand-off, same path
   4. pdnaupd_c/pdneupd_c: 2-D convection-diffusion (dndrv1.f:453-470, rho = 10), row blocks, nev 4 ncv 20 'LM'
   5. pznaupd_c/pzneupd_c: icb_parpack_c.c:104-190 -- diag((i+1)(1+i)), rvec = 0
+  6. BASELINE config 5 at test size: SVD through pdsaupd_c on A^T A, A 20k x 5k with 16 nnz/row ROW-SHARDED over the
+     ranks (all-gather x, local A and A^T products, reduce-scatter; EXAMPLES/SVD/dsvd.f:342-343), hand-off and registered
 
 Run it twice per GPU count: with the peer-memory reductions (default) and with AB200_P2P=0 (ncclAllReduce).
 usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multigpu_check.py"""
@@ -118,7 +120,8 @@ same = (reg.info == 0 and reg.ierr == 0 and reg.nsteps == 0 and counts_of(reg) =
 report("registered halo operator", same, f"counts={counts_of(reg)} hand-offs={reg.nsteps}")
 
 # ---- 4. pdnaupd_c: convection-diffusion, row blocks; the caller's OP gathers x over NCCL ----
-m = 30
+m = 31   # 961 rows: the ranks' row counts differ, and some are odd -- those ranks cannot use the TMA-tiled kernels
+# (16-byte column stride), so the ranks must AGREE not to fuse their reductions (CudaVecOps::ranks_agree_on_fusing)
 S = convdiff2d(m, rho=10.0).tocsr()
 nn = m * m
 f4, c4 = ab.slab_partition(nn, world, rank)
@@ -161,6 +164,30 @@ report("pznaupd_c diag((i+1)(1+i))", g.info == 0 and g.ierr == 0 and err < 1e-5 
        (int(g.nconv), int(g.iparam[2]), int(g.iparam[8])) == (int(o.nconv), int(o.iparam[2]), int(o.iparam[8])) and
        rel <= 1e-10, f"nconv/restarts/nopx gpu={(int(g.nconv), int(g.iparam[2]), int(g.iparam[8]))} "
        f"oracle={(int(o.nconv), int(o.iparam[2]), int(o.iparam[8]))} err={err:.1e} rel vs oracle={rel:.1e}")
+
+# ---- 6. config 5 at test size: row-sharded A^T A under pdsaupd_c ----
+M5, K5 = 20000, 5000
+G5 = ab.GramOperator.randsparse(M5, K5, 16, comm=comm, shard_rows=1500)
+A5 = ab.randsparse_numpy(0, M5, K5, 16)
+k_loc = K5 // world
+r5 = ab.hashed_start_vector_numpy(k_loc, i0=rank * k_loc)
+cnts5 = [k_loc] * world
+
+
+def op5_host(x):   # the oracle's av + atv: gather x, the full product, keep my slice
+    return (A5.T @ (A5 @ host_allgather(x, cnts5)))[rank * k_loc:(rank + 1) * k_loc]
+
+
+o = oracle().solve(op5_host, k_loc, 16, 48, "LM", tol=1e-10, mxiter=3000, resid=r5, c_abi_tol=True)
+for reg in (False, True):
+    g = ab.solve(None if reg else G5, k_loc, 16, 48, "LM", tol=1e-10, mxiter=3000, resid=r5, comm=comm,
+                 registered_op=G5 if reg else None)
+    sg, so = np.sqrt(np.maximum(g.d, 0)), np.sqrt(np.maximum(o.d, 0))
+    rel = np.abs(sg - so).max() / so.max()
+    report(f"pdsaupd_c on row-sharded A^T A ({'registered' if reg else 'hand-off'})",
+           g.info == 0 and g.ierr == 0 and counts_of(g) == counts_of(o) and rel <= 1e-10 and (g.nsteps == 0) == reg,
+           f"counts gpu={counts_of(g)} oracle={counts_of(o)} rel sigma diff={rel:.1e} sigma_max={sg.max():.6f}")
+G5.close()
 
 st = ab.launch_stats()
 print(f"[rank {rank}] launches={st} reductions over: {path}", flush=True)

@@ -6,7 +6,8 @@
 config 2: 2-D Laplacian 4096^2, dsaupd nev=10 ncv=40 'LA'       (converges very slowly by nature: budgeted window)
 config 3: 3-D Laplacian 512^3, pdsaupd-style nev=20 ncv=64 'LA'
 config 4: 2-D convection-diffusion nx=2048 rho=100, dnaupd nev=6 ncv=30 'LR'
-config 5: SVD via dsaupd on A^T A, A random sparse 20M x 5M with 16 nnz/row, nev=16 ncv=48 'LM' (single GPU here)
+config 5: SVD via dsaupd on A^T A, A random sparse 20M x 5M with 16 nnz/row (splitmix64 rule of SURVEY 8d), nev=16 ncv=48
+          'LM'; A row-sharded over the ranks (all-gather x, local A and A^T, reduce-scatter), L2-sized shards per GPU
 """
 import argparse
 import json
@@ -64,28 +65,14 @@ def main():
         name = f"2-D convection-diffusion {nx}^2 rho=100"
     elif args.config == 5:
         m, k, per = int(20_000_000 * args.scale), int(5_000_000 * args.scale), 16
-        g = torch.Generator(device="cuda").manual_seed(0x5EED)
-        cols = torch.randint(0, k, (m * per,), device="cuda", generator=g, dtype=torch.int64)
-        vals = torch.rand(m * per, device="cuda", generator=g, dtype=torch.float64) * 2 - 1
-        rowptr = (torch.arange(0, m + 1, device="cuda", dtype=torch.int64) * per).to(torch.int32)
-        Aop = ab.CsrOperator(m, rowptr, cols.to(torch.int32), vals, ncols=k)
-        # A^T in CSR: sort the entries by column
-        order = torch.argsort(cols, stable=True)
-        rows_of = (torch.arange(0, m * per, device="cuda", dtype=torch.int64) // per)[order].to(torch.int32)
-        counts = torch.bincount(cols, minlength=k)
-        rowptr_t = torch.zeros(k + 1, dtype=torch.int64, device="cuda")
-        rowptr_t[1:] = torch.cumsum(counts, 0)
-        ATop = ab.CsrOperator(k, rowptr_t.to(torch.int32), rows_of, vals[order].contiguous(), ncols=m)
-        del cols, order, counts
-        tmp = torch.empty(m, dtype=torch.float64, device="cuda")
-
-        def op(x, y, *_):  # OP = A^T A as EXAMPLES/SVD/dsvd.f:342-343
-            Aop(x, tmp)
-            ATop(tmp, y)
-        n, nev, ncv, which = k, 16, 48, args.which or "LM"
-        r0 = ab.hashed_start_vector(n)
-        name = f"SVD A^T A, A random sparse {m}x{k}, {per} nnz/row"
+        k -= k % world
+        # A row-sharded over the ranks (and cut into L2-sized shards on each), vectors sharded k/world per rank
+        op = ab.GramOperator.randsparse(m, k, per, comm=comm)
+        n, nev, ncv, which = op.n, 16, 48, args.which or "LM"
+        r0 = ab.hashed_start_vector(n, i0=rank * n)
+        name = f"SVD A^T A, A random sparse {m}x{k} (splitmix64 rule), {per} nnz/row, row-sharded over {world} GPU(s)"
         extra["nnz"] = m * per
+        extra["shards_on_this_rank"] = len(op._keep)
     else:
         raise SystemExit("config must be 2..5")
     torch.cuda.synchronize()
