@@ -184,7 +184,26 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, u
                : "memory");
 }
 
-template <typename T, int ROWS, int EPT, int NST, bool FUSED>
+// OWN (default): the consumers do not park products at all -- thread t reads the entries of ITS row straight from the
+// staged slice (row lengths of the target operators are <= EPT, consecutive rows start ~EPT entries apart, an odd
+// stride for the stencils: conflict-free), gathers x and sums in entry order.  Per entry that is two shared-memory
+// loads and one gather instead of two loads, one store, one more load and a named barrier per block: the kernel was
+// bound by L1/LSU throughput (ncu: l1tex 82 %, DRAM 69 %), not by DRAM.  Products and sums are rounded separately
+// (no FMA contraction) so that every variant returns the same bits.
+template <typename T>
+__device__ __forceinline__ T mul_rn(T a, T b);
+template <>
+__device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T add_rn(T a, T b);
+template <>
+__device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <>
+__device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+
+template <typename T, int ROWS, int EPT, int NST, bool FUSED, bool OWN>
 __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const int* __restrict__ rowptr,
                                                              const int* __restrict__ col, const T* __restrict__ val,
                                                              const T* __restrict__ x, T* __restrict__ y, int nloc,
@@ -261,6 +280,70 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
+    }
+  } else if (OWN) {
+    // ---------------- consumers, row-owner form: thread t reads row r0 + t from the staged slice ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gstep) {
+      tma::mbar_wait(&full[stage], phase);
+      Stage* st = &stages[stage];
+      const int r0 = blk * ROWS;
+      const int nr = (nrows - r0 < ROWS) ? (nrows - r0) : ROWS;
+      int p0, p1, rs, re;
+      if (nrows + 1 - r0 >= ROWS + 4) {
+        p0 = st->rp[0]; p1 = st->rp[ROWS]; rs = st->rp[tid]; re = st->rp[tid + 1];
+      } else {
+        p0 = __ldg(rowptr + r0);
+        p1 = __ldg(rowptr + r0 + nr);
+        rs = (tid < nr) ? __ldg(rowptr + r0 + tid) : p1;
+        re = (tid < nr) ? __ldg(rowptr + r0 + tid + 1) : p1;
+      }
+      T xrow = T(0);
+      if (FUSED && tid < nr) xrow = xs * x[r0 + tid];
+      const int sidx = p0 & ~3;
+      int clen = ((p1 + 3) & ~3);
+      clen = (clen > nnz4 ? nnz4 : clen) - sidx;   // entries of the slice that were staged
+      if (p1 - sidx > CAP) clen = 0;               // oversized block: nothing was staged, everything comes from global
+      T acc = T(0);
+      // the first EPT entries of my row: columns and values first, then all gathers in flight at once
+      int cc[EPT];
+      T vv[EPT], xx[EPT];
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const int q = rs + k, i = q - sidx;
+        cc[k] = 0;
+        vv[k] = T(0);
+        if (q < re) {
+          if (i < clen) { cc[k] = st->col[i]; vv[k] = st->val[i]; }
+          else { cc[k] = __ldg(col + q); vv[k] = __ldg(val + q); }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < EPT; ++k)
+        xx[k] = (rs + k < re) ? ((xh != nullptr && cc[k] >= nloc) ? xh[cc[k] - nloc] : x[cc[k]]) : T(0);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k)
+        if (rs + k < re) acc = add_rn(acc, mul_rn(vv[k], xx[k]));
+      for (int q = rs + EPT; q < re; ++q) {   // rows longer than EPT entries
+        const int i = q - sidx;
+        const int c = (i < clen) ? st->col[i] : __ldg(col + q);
+        const T v = (i < clen) ? st->val[i] : __ldg(val + q);
+        const T xv = (xh != nullptr && c >= nloc) ? xh[c - nloc] : x[c];
+        acc = add_rn(acc, mul_rn(v, xv));
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) tma::mbar_arrive(&empty[stage]);
+      if (FUSED) acc *= xs;  // A*(xs*x) = xs*(A*x): one multiply per row instead of one per entry
+      if (tid < nr) {
+        y[r0 + tid] = acc;
+        if (FUSED) {
+          if (vj_out != nullptr) vj_out[r0 + tid] = xrow;
+          dxy += xrow * acc;
+          dyy += acc * acc;
+        }
+      }
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ---------------- consumers: thread t owns row r0 + t ----------------
@@ -388,25 +471,27 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
   tma::finish_grid_reduce(partial, 2, 2, dots_out, ticket);
 }
 
-template <typename T, int ROWS, int EPT, int NST, bool FUSED>
+template <typename T, int ROWS, int EPT, int NST, bool FUSED, bool OWN>
 int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long nnz, const int* rowptr, const int* col,
                          const T* val, const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial,
                          T* dots_out, unsigned int* ticket, const StepGate<T>& gate, const T* stop) {
   using Stage = SpmvBulkStage<T, ROWS, ROWS * EPT>;
   constexpr size_t smem = sizeof(Stage) * NST + 2 * NST * sizeof(uint64_t);
-  auto kern = k_csr_spmv_bulk<T, ROWS, EPT, NST, FUSED>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  auto kern = k_csr_spmv_bulk<T, ROWS, EPT, NST, FUSED, OWN>;
+  static bool attr_done[tma::kMaxDevices] = {};   // (function, device) attribute
+  static int sms_of[tma::kMaxDevices] = {};
+  const int slot = tma::current_device_slot();
+  if (!attr_done[slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    attr_done = true;
+    attr_done[slot] = true;
   }
-  static int sms = 0;
-  if (!sms) {
+  if (!sms_of[slot]) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+    cudaDeviceGetAttribute(&sms_of[slot], cudaDevAttrMultiProcessorCount, dev);
+    if (sms_of[slot] <= 0) sms_of[slot] = 148;
   }
+  const int sms = sms_of[slot];
   const long long nblk = ((long long)nrows + ROWS - 1) / ROWS;
   long long g = (long long)sms * ctas_per_sm;
   if (g > nblk) g = nblk;
@@ -419,7 +504,7 @@ int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long n
 
 // the bulk kernel needs 16-byte aligned CSR arrays (cp.async.bulk) and the true nnz
 inline bool spmv_bulk_ok(const int* rowptr, const int* col, const void* val, long long nnz) {
-  return spmv_variant() == 0 && nnz > 0 && (((uintptr_t)rowptr | (uintptr_t)col | (uintptr_t)val) & 15u) == 0;
+  return (spmv_variant() == 0 || spmv_variant() == 4) && nnz > 0 && (((uintptr_t)rowptr | (uintptr_t)col | (uintptr_t)val) & 15u) == 0;
 }
 
 template <typename T, bool FUSED>
@@ -427,9 +512,20 @@ int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr
                      const T* x, T* y, int nloc, const T* xh, T xs, T* vj_out, T* partial, T* dots_out,
                      unsigned int* ticket, const StepGate<T>& gate = StepGate<T>(), const T* stop = nullptr) {
   static const int variant = getenv("AB200_SPMV_BULK") ? atoi(getenv("AB200_SPMV_BULK")) : 0;
+  // row-owner consumers (default) or the product-parking form (AB200_SPMV_OWN=0 / ab200_set_spmv_variant(4))
+  // measured (B200, SpMV alone): 5-point 2-D stencil 6.07 TB/s row-owner vs 5.63 parked; 7-point 3-D stencil 4.84 vs
+  // 5.25 (the 8 entries per thread cost 72 registers: one CTA per SM less) -- so the row-owner form is the default
+  // where rows hold fewer than six entries; AB200_SPMV_OWN=2 forces it everywhere, =0 switches it off
+  static const int own_env = getenv("AB200_SPMV_OWN") ? atoi(getenv("AB200_SPMV_OWN")) : 1;
+  const double avg_rows = (double)nnz / (double)(nrows > 0 ? nrows : 1);
+  const bool own = own_env != 0 && spmv_variant() != 4 && (avg_rows <= 5.9 || own_env == 2);
 #define AB200_BULK_CFG(ROWS_, EPT_, NST_, CTAS_)                                                                    \
-  return launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, xh, xs,  \
-                                                           vj_out, partial, dots_out, ticket, gate, stop)
+  return own ? launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED, true>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, \
+                                                                       xh, xs, vj_out, partial, dots_out, ticket, gate,  \
+                                                                       stop)                                             \
+             : launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED, false>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y,     \
+                                                                        nloc, xh, xs, vj_out, partial, dots_out, ticket, \
+                                                                        gate, stop)
   // entries per thread and ring slot: a 256-row block of a matrix with avg entries per row holds ~256*avg (+3 of
   // alignment pad); 6 covers 5-point stencils, 8 covers 7-point stencils
   const double avg = (double)nnz / (double)(nrows > 0 ? nrows : 1);
@@ -743,7 +839,7 @@ using namespace ab200;
 extern "C" {
 
 
-void ab200_set_spmv_variant(int variant) { spmv_variant() = (variant >= 0 && variant <= 2) ? variant : 0; }
+void ab200_set_spmv_variant(int variant) { spmv_variant() = (variant >= 0 && variant <= 4) ? variant : 0; }
 
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y) {
   return launch_spmv<double>(nrows, rowptr, col, val, x, y, 0, nullptr, nnz_of(nrows, rowptr));

@@ -99,6 +99,15 @@ __device__ void finish_grid_reduce(T* partial, int pcols, int ncols, T* out, uns
   if (fused) peer_publish(*pub);
 }
 
+// per-function launch attributes (dynamic shared memory size) belong to a (function, device) pair: a process that
+// drives several GPUs must set them once per device, not once per process
+constexpr int kMaxDevices = 16;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return (dev < 0 ? 0 : dev) % kMaxDevices;
+}
+
 // ---- host: tensor-map descriptors, cached (the encode call is a driver round trip of ~0.4 ms) ----
 // 2-D map over a column-major n x ncols matrix (leading dimension ldv), box = box_rows x box_cols;
 // ncols == 0 -> 1-D map over a vector of n elements, box = box_rows.

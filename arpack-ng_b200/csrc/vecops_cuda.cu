@@ -817,7 +817,11 @@ void CudaVecOps<T>::vq_update(int64_t n, int kin, int kout, T* v, int64_t ldv, c
     if (with_resid) axpby_norm(n, sigma, T(0), nullptr, resid, mb_nrm2);
     return;
   }
+  resolve_pending();
   T* qdev = stage_matrix(q_host, kin, kout, ldq);
+  if (kernel_mode_ == 0 && vq_mma(n, kin, kout, v, ldv, qdev, q_host, ldq, v, ldv, with_resid, sigma, beta, beta_col,
+                                  resid, mb_nrm2))
+    return;
   if (kernel_mode_ == 0 && vq_tma(n, kin, kout, v, ldv, qdev, v, ldv, with_resid, sigma, beta, beta_col, resid,
                                   mb_nrm2))
     return;
@@ -835,7 +839,11 @@ template <typename T>
 void CudaVecOps<T>::vq_out(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* m_host, int ldm,
                            T* out, int64_t ldo) {
   if (kout <= 0) return;
+  resolve_pending();
   T* qdev = stage_matrix(m_host, kin, kout, ldm);
+  if (kernel_mode_ == 0 &&
+      vq_mma(n, kin, kout, v, ldv, qdev, m_host, ldm, out, ldo, false, T(0), T(0), -1, nullptr, nullptr))
+    return;
   if (kernel_mode_ == 0 &&
       vq_tma(n, kin, kout, v, ldv, qdev, out, ldo, false, T(0), T(0), -1, nullptr, nullptr))
     return;

@@ -200,6 +200,9 @@ class CudaVecOps final : public VecOps<T> {
   bool dots_tma(int64_t n, int j, const T* v, int64_t ldv, const T* x, const T* y, T* mb_out);
   bool vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* qdev, T* out, int64_t ldo,
               bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2);
+  // FP64 tensor-core form of the same update (vq_mma.cu); false: not applicable (FP32, layout) -> vq_tma / generic
+  bool vq_mma(int64_t n, int kin, int kout, const T* v, int64_t ldv, const T* qdev, const T* q_host, int ldq, T* out,
+              int64_t ldo, bool with_resid, T sigma, T beta, int beta_col, T* resid, T* mb_nrm2);
 };
 
 }  // namespace ab200

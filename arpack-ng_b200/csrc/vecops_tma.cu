@@ -623,15 +623,16 @@ bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, Orth
   } else {
     xmap = map;
   }
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};   // the attribute belongs to (function, device)
+  const int dev = current_device_slot();
   const size_t smem = (size_t)p.nstages * p.stage_bytes + aux_bytes<T>();
-  if (!attr_set) {
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(k_orth<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(kTileBudget + aux_bytes<T>())) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int64_t ntiles = (p.n + R - 1) / R;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
@@ -646,14 +647,15 @@ bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, Orth
 template <typename T, bool SPEC, int KB>
 bool launch_upd_kb(cudaStream_t stream, int grid, size_t smem, const CUtensorMap& map, const CUtensorMap& xmap,
                    const OrthParams<T>& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(k_upd<T, SPEC, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(kTileBudget + aux_bytes<T>())) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   k_upd<T, SPEC, KB><<<grid, kThreadsTma, smem, stream>>>(map, xmap, p);
   return true;
@@ -807,7 +809,8 @@ bool CudaVecOps<T>::vq_tma(int64_t n, int kin, int kout, const T* v, int64_t ldv
   p.partial = partial_;
   const size_t smem = (size_t)p.nstages * p.stage_bytes + aux_bytes_vq<T>();
   const int smem_max = (int)(kTileBudgetVq + aux_bytes_vq<T>());
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set_dev[kMaxDevices][3] = {};
+  bool* attr_set = attr_set_dev[current_device_slot()];
   const int ai = rpl == 4 ? 2 : (rpl == 2 ? 1 : 0);
   if (!attr_set[ai]) {
     cudaError_t e = cudaSuccess;

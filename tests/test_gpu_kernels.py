@@ -107,6 +107,35 @@ def test_vq_update_kernels(ab, mode, n, kin, kout, beta_col):
         L.ab200_set_kernel_mode(0)
 
 
+@pytest.mark.parametrize("kin,kout,npx", [(64, 21, 44), (40, 11, 30), (64, 31, 33), (24, 9, 2)])
+def test_vq_update_banded_q_as_the_restart_produces_it(ab, kin, kout, npx):
+    """After dsapps' QR sweeps column c of Q is zero below row np + c (dsapps.f:461 multiplies kplusp-i+1 entries only):
+    the tensor-core kernel skips the k-steps that hold nothing but those zeros (vq_mma.cu) -- same result."""
+    import torch
+    L = ab.lib()
+    n = 50000 + 37
+    g = torch.Generator(device="cuda").manual_seed(5 + kin)
+    ldv = n + (n & 1)
+    Vfull = torch.zeros(ldv * kin, dtype=torch.float64, device="cuda")
+    V = Vfull.view(kin, ldv)[:, :n]
+    V.copy_(torch.randn(kin, n, dtype=torch.float64, device="cuda", generator=g))
+    V0 = V.clone()
+    Qh = np.random.default_rng(kin * kout).standard_normal((kin, kout))
+    for c in range(kout):
+        Qh[npx + c + 1:, c] = 0.0
+    resid = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    r0 = resid.clone()
+    nrm2 = np.zeros(1)
+    qcm = np.asfortranarray(Qh)
+    assert L.ab200_debug_vq_f64(n, kin, kout, Vfull.data_ptr(), ldv, qcm.ctypes.data, 0.5, 2.0, kout - 1,
+                                resid.data_ptr(), nrm2.ctypes.data) == 0
+    ref = torch.as_tensor(Qh, device="cuda").T @ V0
+    assert torch.allclose(V[:kout], ref, rtol=0, atol=1e-12 * float(V0.abs().max()) * kin)
+    rr = 0.5 * r0 + 2.0 * ref[kout - 1]
+    assert torch.allclose(resid, rr, rtol=0, atol=1e-12 * float(rr.abs().max()))
+    assert abs(nrm2[0] - float(rr @ rr)) <= 1e-11 * float(rr @ rr)
+
+
 def test_reductions_are_bit_reproducible(ab):
     """Deterministic grids and trees: the same call twice gives the same bits (no floating-point atomics)."""
     import torch
@@ -168,7 +197,7 @@ def test_csr_spmv_variants_ragged(ab, nrows, seed, heavy):
     L = ab.lib()
     out = {}
     try:
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 4):
             L.ab200_set_spmv_variant(variant)
             y = torch.full((nrows,), float("nan"), dtype=torch.float64, device="cuda")
             assert L.ab200_csr_spmv_f64(nrows, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(),
@@ -179,7 +208,8 @@ def test_csr_spmv_variants_ragged(ab, nrows, seed, heavy):
         L.ab200_set_spmv_variant(0)
     m = min(nrows, 5000)
     assert np.array_equal(out[0][:m], ref[:m])          # bulk: in-order row sums, bit for bit
-    assert np.array_equal(out[0], out[1])               # bulk == stream everywhere
+    assert np.array_equal(out[0], out[1])               # bulk (row-owner consumers) == stream everywhere
+    assert np.array_equal(out[0], out[4])               # == bulk with parked products
     full = S @ xs
     assert np.allclose(out[2], full, rtol=1e-13, atol=1e-14)
     assert np.allclose(out[0], full, rtol=1e-13, atol=1e-14)
