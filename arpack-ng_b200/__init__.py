@@ -102,6 +102,7 @@ def lib():
     L.ab200_set_stream.argtypes = [vp]
     L.ab200_get_stream.restype = vp
     L.ab200_set_kernel_mode.argtypes = [C.c_int]
+    L.ab200_set_compat.argtypes = [C.c_int]
     L.ab200_release.argtypes = [vp]
     L.ab200_launch_stats.argtypes = [C.POINTER(C.c_ulonglong)]
     L.ab200_device_count.restype = C.c_int

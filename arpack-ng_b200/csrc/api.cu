@@ -43,6 +43,7 @@ constexpr int kInfoDeviceError = -9990;
 
 cudaStream_t g_stream = 0;
 int g_kernel_mode = 0;
+int g_compat = 0;  // ab200_set_compat(): bit 0 = maintain workd(ipntr(3)) in mode 1
 std::mutex g_mu;
 
 // COMMON /debug/ (debug.h) and the counters of COMMON /timing/ (stat.h) of the last solve
@@ -267,6 +268,8 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
         registered_ops<T>().erase(workl);  // not applicable to this solve (bmat='G', modes 2-5)
         registered_grams().erase(workl);
       }
+      if (SYM) c->sym->set_keep_bx((g_compat & 1) != 0);
+      else c->nonsym->set_keep_bx((g_compat & 1) != 0);
       // device-resident sweeps (no host round trip per step) need hand-off slots the device reaches by itself: a
       // device-resident workd, or a registered operator (then no hand-off happens at all)
       {
@@ -584,6 +587,7 @@ void stat_c(a_int* nopx, a_int* nbx, a_int* nrorth, a_int* nitref, a_int* nrstrt
 void ab200_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 void* ab200_get_stream(void) { return (void*)g_stream; }
 void ab200_set_kernel_mode(int mode) { g_kernel_mode = mode; }
+void ab200_set_compat(int flags) { g_compat = flags; }
 void ab200_release(const void* workl) {
   release_cplx(workl);
   std::lock_guard<std::mutex> lk(g_mu);

@@ -107,6 +107,9 @@ class IrlBase {
   long long host_round_trips() const { return cnt_round_trips_; }
   // deferral needs hand-off slots the device can reach without the host (device-resident workd or a registered OP)
   void set_deferral(bool on) { defer_enabled_ = on; }
+  // compatibility option: also maintain workd(ipntr(3)) = B*x = x in mode 1 (dsaitr.f:517 fills it; nothing in mode 1
+  // reads it, so by default the store -- one more n-vector per step -- is skipped)
+  void set_keep_bx(bool on) { keep_bx_ = on; }
   bool has_registered_op() const { return (bool)op_; }
   using FusedOp = std::function<bool(T inv, const StepGate<T>* gate, const T* resid, T* vj, T* y, T* mb_dots)>;
   void set_registered_op(std::function<void(const T*, T*)> op, FusedOp fused) {
@@ -164,6 +167,7 @@ class IrlBase {
   bool ai_fused_op_ = false;
   // device-resident batch state
   bool defer_enabled_ = false;
+  bool keep_bx_ = false;
   int df_first_ = 0, df_last_ = 0, df_j_ = 0;
   std::vector<char> df_fused_;
   long long cnt_deferred_steps_ = 0, cnt_deferred_trips_ = 0, cnt_round_trips_ = 0;
@@ -237,6 +241,7 @@ class IrlBase {
       ops_->dot(n_, resid_, resid_, mbC());
     }
     gv_rnorm0_ = fetch_norm_from_dot(mbC());
+    if (bmat_ == 'I' && gv_j_ == 1 && (!std::isfinite(gv_rnorm0_) || gv_rnorm0_ == T(0))) rescale_start_vector();
     rnorm_ = gv_rnorm0_;
     if (gv_j_ > 1) {
       // orthogonalise against V(:,1:j-1) with iterative refinement (dgetv0.f:326-397)
@@ -270,6 +275,26 @@ class IrlBase {
     if (trace_levels().mgetv0 > 0 && ops_->rank() == 0)  // dgetv0.f:398-401
       trace::dvout1(rnorm_, "_getv0: B-norm of initial / restarted starting vector");
     CO_END(gv_pc_)
+  }
+
+  // The norms of this library are square roots of sums of squares; pdnorm2.f:72-80 (and the BLAS dnrm2 behind the
+  // sequential code) divide by the largest entry first, so they survive start vectors whose squares overflow or
+  // underflow.  Same result here for the only vector the caller controls: when the sum of squares of the start vector
+  // is not a normal number, scale the vector by the power of two that brings its largest entry to [1, 2) -- an exact
+  // operation that leaves the first Lanczos vector resid/||resid|| unchanged -- and take the norm again.
+  void rescale_start_vector() {
+    const int nr = ops_->nranks();
+    ops_->zero((int64_t)nr, mbA());
+    if (!ops_->absmax(n_, resid_, mbA() + ops_->rank())) return;
+    ops_->allreduce_sum(mbA(), (size_t)nr);   // every rank filled its own slot: the sum is a gather
+    ops_->fetch(hA(), mbA(), (size_t)nr);
+    cnt_round_trips_++;
+    T amax = T(0);
+    for (int r = 0; r < nr; ++r) amax = std::max(amax, hA()[r]);
+    if (!(amax > T(0)) || !std::isfinite(amax)) return;   // a genuinely zero (or non-finite) vector: as the reference
+    ops_->scal(n_, std::ldexp(T(1), -std::ilogb(amax)), resid_);
+    ops_->dot(n_, resid_, resid_, mbC());
+    gv_rnorm0_ = fetch_norm_from_dot(mbC());
   }
 
   // trace level of the step routine: msaitr (symmetric) or mnaitr (nonsymmetric)
@@ -392,11 +417,13 @@ class IrlBase {
             }
             // v_j = r/||r||, x = v_j (dsaitr.f:438-468); with a registered operator K1+K2+K3 are one kernel
             bool fused = false;
-            if (fused_op_) fused = fused_op_(first ? T(1) / rnorm_ : T(0), first ? nullptr : &g, resid_, vcol(df_j_),
-                                             slot(irj()), sC + 2);
+            if (fused_op_ && !keep_bx_)
+              fused = fused_op_(first ? T(1) / rnorm_ : T(0), first ? nullptr : &g, resid_, vcol(df_j_), slot(irj()),
+                                sC + 2);
             if (!fused) {
-              if (first) ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(df_j_), slot(ivj()), nullptr, true);
-              else ops_->start_step_gated(n_, g, resid_, vcol(df_j_), slot(ivj()), nullptr);
+              T* bx = keep_bx_ ? slot(IPJ) : nullptr;
+              if (first) ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(df_j_), slot(ivj()), bx, true);
+              else ops_->start_step_gated(n_, g, resid_, vcol(df_j_), slot(ivj()), bx);
             }
             df_fused_[s] = fused ? 1 : 0;
             if (op_ && !fused) op_(slot(ivj()), slot(irj()));
@@ -444,7 +471,7 @@ class IrlBase {
       }
       // v_j = r/||r||, p_j = B r/||r||, x = v_j   (dsaitr.f:438-468)
       ai_fused_op_ = false;
-      if (fused_op_ && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm()) {
+      if (fused_op_ && !keep_bx_ && bmat_ == 'I' && mode_ == 1 && rnorm_ >= tiny_norm()) {
         // registered operator: K1+K2+K3 in one kernel (v_j written on the way, x never materialised)
         ai_fused_op_ = fused_op_(T(1) / rnorm_, nullptr, resid_, vcol(ai_j_), slot(irj()), mbC() + 2);
       }
@@ -454,7 +481,7 @@ class IrlBase {
           // mode 1 / bmat 'I': the B*x slot is neither read by this code nor part of the hand-off (ipntr(3) is
           // documented for the shift-invert modes only), so the third store of K2 is skipped
           ops_->start_step(n_, T(1) / rnorm_, resid_, vcol(ai_j_), slot(ivj()),
-                           (bmat_ == 'I' && mode_ == 1) ? nullptr : slot(IPJ), bmat_ == 'I');
+                           (bmat_ == 'I' && mode_ == 1 && !keep_bx_) ? nullptr : slot(IPJ), bmat_ == 'I');
         } else {
           // dlascl fallback of the reference (dsaitr.f:450-453): scale in two safe steps
           const T big = std::ldexp(T(1), sizeof(T) == 8 ? 500 : 60);

@@ -87,6 +87,8 @@ struct VecOps {
   virtual void axpby_norm(int64_t n, T a, T b, const T* x, T* y, T* mb_nrm2_out) = 0;
   // mb_out[0] = sum x_i*y_i
   virtual void dot(int64_t n, const T* x, const T* y, T* mb_out) = 0;
+  // mb_out[0] = max |x_i| (local rows).  false: not provided by this backend.
+  virtual bool absmax(int64_t /*n*/, const T* /*x*/, T* /*mb_out*/) { return false; }
   // LAPACK xLARNV(idist=2) stream (dgetv0.f:236): x_i uniform(-1,1); iseed is advanced on the host
   virtual void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) = 0;
   // K1+K2 (dsaitr.f:438-442,464): vj = resid*inv ; out_x = vj ; if bx != nullptr: bx *= inv

@@ -273,6 +273,43 @@ __global__ void __launch_bounds__(kThreads) k_dot(int64_t n, const T* __restrict
   finish_grid_reduce(partial, 1, 1, out, ticket);
 }
 
+// max |x_i|: per-CTA maxima, combined by the CTA that takes the last ticket (max is order-independent)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_absmax(int64_t n, const T* __restrict__ x, T* __restrict__ partial,
+                                                     T* __restrict__ out, unsigned int* ticket) {
+  __shared__ T red[kWarps];
+  __shared__ bool s_last;
+  T m = T(0);
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    const T a = fabs(x[r]);
+    m = (a > m || a != a) ? a : m;   // a NaN entry propagates
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (other > m || other != other) ? other : m;
+  }
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kWarps; ++w) m = (red[w] > m || red[w] != red[w]) ? red[w] : m;
+    partial[blockIdx.x] = m;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (s_last) {
+      __threadfence();
+      T g = T(0);
+      for (unsigned int b = 0; b < gridDim.x; ++b) {
+        const T v = ld_cg(partial + b);
+        g = (v > g || v != v) ? v : g;
+      }
+      *out = g;
+      *ticket = 0u;
+    }
+  }
+}
+
 // y = a*y + b*x (+ ||y||^2)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_axpby_norm(int64_t n, T a, T b, const T* __restrict__ x, T* y,
@@ -691,6 +728,15 @@ void CudaVecOps<T>::dot(int64_t n, const T* x, const T* y, T* out) {
   ProfScope ps(stream_, "dot", (double)sizeof(T) * n * (x == y ? 1.0 : 2.0));
   k_dot<T><<<grid, kThreads, 0, stream_>>>(n, x, y, partial_, out, ticket_);
   AB200_LAUNCHED();
+}
+
+template <typename T>
+bool CudaVecOps<T>::absmax(int64_t n, const T* x, T* out) {
+  const int grid = reduce_grid(n);
+  ensure_partial((size_t)grid);
+  k_absmax<T><<<grid, kThreads, 0, stream_>>>(n, x, partial_, out, ticket_);
+  AB200_LAUNCHED();
+  return true;
 }
 
 template <typename T>

@@ -109,6 +109,7 @@ class CudaVecOps final : public VecOps<T> {
   void scal(int64_t n, T alpha, T* x) override;
   void axpby_norm(int64_t n, T a, T b, const T* x, T* y, T* mb_nrm2_out) override;
   void dot(int64_t n, const T* x, const T* y, T* mb_out) override;
+  bool absmax(int64_t n, const T* x, T* mb_out) override;
   void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
   void start_step(int64_t n, T inv_rnorm, const T* resid, T* vj, T* out_x, T* bx, bool bx_from_resid) override;
   bool deferred_ok() const override { return true; }

@@ -195,6 +195,11 @@ void* ab200_get_stream(void);
 /* 0 = automatic (TMA-tiled kernels when the layout allows), 1 = generic kernels only */
 void ab200_set_kernel_mode(int mode);
 /* free the device mirrors / solver state keyed to this workl (also done when workl is reused with ido = 0) */
+/* Compatibility switches for callers that rely on side effects of the reference the hot path does not need (default 0):
+ *   bit 0: maintain workd(ipntr(3)) = B*x (= x) at every ido = 1 hand-off of mode 1 as SRC/dsaitr.f:517 / dnaitr.f:505
+ *          does; by default that slot is only written where the protocol documents it (bmat = 'G', modes 2-5), which
+ *          saves one n-vector store per Lanczos step.  Applies to solves started (ido = 0) after the call. */
+void ab200_set_compat(int flags);
 void ab200_release(const void* workl);
 void ab200_release_all(void);
 /* out4 = {kernels launched, all-reduces issued, TMA-path launches, generic-path launches} since load */

@@ -81,6 +81,12 @@ struct HostVecOps final : VecOps<T> {
     for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
     *out = s;
   }
+  bool absmax(int64_t n, const T* x, T* out) override {
+    T m = 0;
+    for (int64_t i = 0; i < n; ++i) m = std::max(m, std::fabs(x[i]));
+    *out = m;
+    return true;
+  }
   void larnv_uniform_m1_1(int64_t n, int iseed[4], T* x) override;
   void start_step(int64_t n, T inv, const T* resid, T* vj, T* outx, T* bx, bool from_resid) override {
     if (halted()) return;

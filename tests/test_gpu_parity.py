@@ -359,3 +359,69 @@ def test_cuda_path_reproduces_committed_scipy_arpack_vectors(ab, c, registered):
     r = ab.solve(None if registered else A, A.n, c["nev"], c["ncv"], c["which"], sym=c["sym"], tol=c["tol"],
                  mxiter=3000, resid=golden_cases.start_vector(c, A.n), registered_op=A if registered else None)
     golden_cases.check_against_golden(c, r, c["nev"])
+
+
+# --------------------------------------------------------------------------------------------------
+# round 2: device-resident sweeps, compatibility switch, start-vector rescue
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sym", [True, False])
+def test_device_resident_sweeps_take_the_oracles_path_with_one_round_trip_per_sweep(ab, sym):
+    """IrlBase::extend, deferred mode on the GPU: same counts and eigenvalues as the oracle, and far fewer blocking
+    mailbox reads than Lanczos steps (ab200_host_round_trips)."""
+    if sym:
+        A, S, nev, ncv, which = ab.CsrOperator.laplace2d(61, 47), laplace2d(61, 47), 5, 24, "LA"
+    else:
+        A, S, nev, ncv, which = ab.CsrOperator.convdiff2d(40, rho=10.0), convdiff2d(40, rho=10.0), 4, 20, "LM"
+    n = A.n
+    r0 = np.random.default_rng(31).uniform(-1, 1, n)
+    rt0 = ab.host_round_trips()
+    g = ab.solve(A, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=3000, resid=r0, eupd=False)
+    trips = ab.host_round_trips() - rt0
+    o = Oracle().solve(lambda x: S @ x, n, nev, ncv, which, sym=sym, tol=1e-10, mxiter=3000, resid=r0, c_abi_tol=True,
+                       eupd=False)
+    assert g.info == o.info == 0 and _counts(g) == _counts(o)
+    nopx, sweeps = int(g.iparam[8]), int(g.iparam[2]) + 1
+    assert trips <= 3 * sweeps + 6 and trips < nopx // 3
+
+
+def test_compat_switch_maintains_the_bx_slot_in_mode_1(ab):
+    """ab200_set_compat(1): workd(ipntr(3)) = B*x = x at every ido = 1 hand-off, as dsaitr.f:517 leaves it; path and
+    results are unchanged."""
+    torch = _torch()
+    A = ab.CsrOperator.laplace2d(33, 29)
+    n = A.n
+    r0 = np.random.default_rng(8).uniform(-1, 1, n)
+    seen = []
+
+    def op(x, y, *_):
+        A(x, y)
+        seen.append((x.clone(), None))
+    base = ab.solve(A, n, 4, 16, "LA", tol=1e-10, mxiter=500, resid=r0)
+    L = ab.lib()
+    L.ab200_set_compat(1)
+    try:
+        checks = []
+        v, workd, res = ab.alloc_device_buffers(n, 16)
+
+        def op2(x, y, *_):
+            A(x, y)
+            checks.append(bool(torch.equal(workd[:n], x)))   # ipntr(3) = 1 in mode 1: the first slot of workd
+        r = ab.solve(op2, n, 4, 16, "LA", tol=1e-10, mxiter=500, resid=r0, buffers=(v, workd, res))
+    finally:
+        L.ab200_set_compat(0)
+    assert r.info == 0 and _counts(r) == _counts(base)
+    assert np.array_equal(r.d, base.d)
+    assert len(checks) > 10 and all(checks[1:])               # (the first product is dgetv0's, ido = -1)
+
+
+@pytest.mark.parametrize("scale", [1e200, 1e-200])
+def test_start_vector_whose_squares_overflow_or_underflow_gpu(ab, scale):
+    """IrlBase::rescale_start_vector through the CUDA kernels (k_absmax + exact power-of-two scaling): the oracle's
+    path (pdnorm2.f:72-80 / dnrm2 scale by the largest entry)."""
+    A, S = ab.CsrOperator.laplace2d(31, 23), laplace2d(31, 23)
+    n = A.n
+    r0 = np.random.default_rng(77).uniform(-1, 1, n) * scale
+    g = ab.solve(A, n, 4, 14, "LA", tol=1e-10, mxiter=500, resid=r0)
+    o = Oracle().solve(lambda x: S @ x, n, 4, 14, "LA", tol=1e-10, mxiter=500, resid=r0, c_abi_tol=True)
+    assert g.info == o.info == 0 and _counts(g) == _counts(o)
+    assert np.abs(g.d - o.d).max() <= RTOL64 * np.abs(o.d).max()

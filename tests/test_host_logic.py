@@ -507,3 +507,21 @@ def test_nonsym_complex_shift_real_and_imaginary_part_modes(mode):
             k += 1
         lam = (x.conj() @ (A @ x)) / (x.conj() @ x)
         assert np.abs(ev - lam).min() < 1e-6 or np.abs(ev - np.conj(lam)).min() < 1e-6
+
+
+@pytest.mark.parametrize("scale", [1e200, 1e-200])
+def test_start_vector_whose_squares_overflow_or_underflow(scale):
+    """pdnorm2.f:72-80 and the BLAS dnrm2 behind dgetv0 divide by the largest entry before squaring; this library's
+    norms are plain sums of squares, so a start vector of entries ~1e200 (or ~1e-200) is first scaled by a power of two
+    (IrlBase::rescale_start_vector).  The first Lanczos vector is the same either way: same path, same eigenvalues as the
+    oracle -- and as the run from the unscaled vector."""
+    A = laplace2d(15, 14)
+    n = A.shape[0]
+    r0 = start(n, 21)
+    base = HostDouble().solve(lambda x: A @ x, n, 4, 14, "LA", tol=1e-10, mxiter=500, resid=r0)
+    a = HostDouble().solve(lambda x: A @ x, n, 4, 14, "LA", tol=1e-10, mxiter=500, resid=r0 * scale)
+    b = Oracle().solve(lambda x: A @ x, n, 4, 14, "LA", tol=1e-10, mxiter=500, resid=r0 * scale)
+    assert a.info == b.info == base.info == 0
+    assert counts(a) == counts(b)
+    assert np.abs(a.d - b.d).max() <= 1e-12 * np.abs(b.d).max()
+    assert np.abs(a.d - base.d).max() <= 1e-10 * np.abs(b.d).max()
