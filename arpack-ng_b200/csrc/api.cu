@@ -22,6 +22,7 @@
 #include <memory>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/arpack_b200.h"
 #include "driver.hpp"
@@ -60,9 +61,53 @@ template <typename T> SeedState Globals<T>::seed;
 template <typename T> SeedState Globals<T>::seed_par;
 template <typename T> T Globals<T>::smlnum_first = T(-1);
 
+// Device back-ends are recycled between solves: creating one costs a handful of cudaMalloc / cudaMallocHost calls and
+// destroying it as many cudaFree / cudaFreeHost (each an implicit device synchronisation) -- tens of milliseconds per
+// solve on a busy host, all of it outside any kernel.  A finished solve parks its back-end here; the next solve on
+// the same device, stream and communicator takes it over (mailbox, reduction scratch, pinned staging buffers).
+template <typename T>
+struct OpsPool {
+  struct Item { int dev; cudaStream_t stream; NcclComm* comm; std::unique_ptr<CudaVecOps<T>> ops; };
+  std::vector<Item> items;
+  std::mutex mu;
+  std::unique_ptr<CudaVecOps<T>> take(cudaStream_t stream, NcclComm* comm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < items.size(); ++i)
+        if (items[i].dev == dev && items[i].stream == stream && items[i].comm == comm) {
+          std::unique_ptr<CudaVecOps<T>> o = std::move(items[i].ops);
+          items.erase(items.begin() + (long)i);
+          o->reset_for_reuse();
+          return o;
+        }
+    }
+    return std::make_unique<CudaVecOps<T>>(stream, comm);
+  }
+  void give(std::unique_ptr<CudaVecOps<T>> o, NcclComm* comm) {
+    if (!o) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (items.size() >= 4) items.erase(items.begin());   // oldest out (its destructor frees the device memory)
+    items.push_back(Item{dev, o->stream(), comm, std::move(o)});
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    items.clear();
+  }
+};
+template <typename T>
+OpsPool<T>& ops_pool() {
+  static OpsPool<T> p;
+  return p;
+}
+
 template <typename T>
 struct Ctx {
   std::unique_ptr<CudaVecOps<T>> ops;
+  NcclComm* comm_ptr = nullptr;
   std::unique_ptr<IrlSym<T>> sym;
   std::unique_ptr<IrlNonsym<T>> nonsym;
   bool par = false;
@@ -88,6 +133,9 @@ struct Ctx {
       if (v_host) ops->release(v_d);
       if (workd_host) ops->release(workd_d);
       ops->release(z_mirror);
+      sym.reset();       // the solvers hold a pointer to ops: gone before it changes hands
+      nonsym.reset();
+      ops_pool<T>().give(std::move(ops), comm_ptr);
     }
     for (void* p : csr_mirror)
       if (p) cudaFree(p);
@@ -120,7 +168,8 @@ Ctx<T>* make_ctx(const void* key, bool par, int comm_handle, int n, int ncv, T* 
     comm = comm_from_handle(comm_handle);
     if (!comm) throw CudaError("p*aupd_c: comm is not a handle returned by ab200_comm_create()");
   }
-  c->ops = std::make_unique<CudaVecOps<T>>(g_stream, comm);
+  c->ops = ops_pool<T>().take(g_stream, comm);
+  c->comm_ptr = comm;
   c->ops->set_kernel_mode(g_kernel_mode);
   c->par = par;
   c->n = n;
@@ -602,6 +651,8 @@ void ab200_release_all(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().clear();
   table<float>().clear();
+  ops_pool<double>().clear();
+  ops_pool<float>().clear();
   registered_ops<double>().clear();  // descriptors hold the caller's pointers: none may outlive this call
   registered_ops<float>().clear();
   registered_grams().clear();

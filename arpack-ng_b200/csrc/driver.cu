@@ -513,12 +513,11 @@ int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr
                      unsigned int* ticket, const StepGate<T>& gate = StepGate<T>(), const T* stop = nullptr) {
   static const int variant = getenv("AB200_SPMV_BULK") ? atoi(getenv("AB200_SPMV_BULK")) : 0;
   // row-owner consumers (default) or the product-parking form (AB200_SPMV_OWN=0 / ab200_set_spmv_variant(4))
-  // measured (B200, SpMV alone): 5-point 2-D stencil 6.07 TB/s row-owner vs 5.63 parked; 7-point 3-D stencil 4.84 vs
-  // 5.25 (the 8 entries per thread cost 72 registers: one CTA per SM less) -- so the row-owner form is the default
-  // where rows hold fewer than six entries; AB200_SPMV_OWN=2 forces it everywhere, =0 switches it off
+  // measured (B200, SpMV alone, L2 flushed): 5-point 2-D stencil 6.07 TB/s row-owner vs 5.63 parked; 7-point 3-D stencil
+  // 6.46 vs 5.25 with three CTAs per SM (the 8 entries per thread cost 72 registers: a fourth CTA does not fit, and a
+  // grid of 4 per SM then runs in two uneven waves: 4.84).  AB200_SPMV_OWN=0 switches back to the parked products.
   static const int own_env = getenv("AB200_SPMV_OWN") ? atoi(getenv("AB200_SPMV_OWN")) : 1;
-  const double avg_rows = (double)nnz / (double)(nrows > 0 ? nrows : 1);
-  const bool own = own_env != 0 && spmv_variant() != 4 && (avg_rows <= 5.9 || own_env == 2);
+  const bool own = own_env != 0 && spmv_variant() != 4;
 #define AB200_BULK_CFG(ROWS_, EPT_, NST_, CTAS_)                                                                    \
   return own ? launch_spmv_bulk_cfg<T, ROWS_, EPT_, NST_, FUSED, true>(s, CTAS_, nrows, nnz, rowptr, col, val, x, y, nloc, \
                                                                        xh, xs, vj_out, partial, dots_out, ticket, gate,  \
@@ -541,7 +540,9 @@ int launch_spmv_bulk(cudaStream_t s, int nrows, long long nnz, const int* rowptr
     case 1: AB200_BULK_CFG(128, 8, 3, 4);
     case 2: AB200_BULK_CFG(256, 8, 2, 3);
     case 3: AB200_BULK_CFG(256, 8, 3, 2);
-    default: AB200_BULK_CFG(256, 8, 2, 4);  // measured best on the 7-point Laplacian (5.4 TB/s alone)
+    default:
+      if (own) AB200_BULK_CFG(256, 8, 2, 3);
+      AB200_BULK_CFG(256, 8, 2, 4);  // parked products: measured best on the 7-point Laplacian (5.25 TB/s alone)
   }
 #undef AB200_BULK_CFG
 }

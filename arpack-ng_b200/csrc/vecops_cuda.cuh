@@ -130,6 +130,14 @@ class CudaVecOps final : public VecOps<T> {
 
   cudaStream_t stream() const { return stream_; }
   void set_stream(cudaStream_t s) { stream_ = s; }
+  // a recycled back-end starts a new solve: nothing of the previous one may leak into it
+  void reset_for_reuse() {
+    stop_ = nullptr;
+    has_pending_ = false;
+    agreed_v_ = nullptr;
+    agreed_ldv_ = -1;
+    agreed_fuse_ = false;
+  }
   // 0 = auto (TMA-tiled kernels when the layout allows), 1 = force the generic kernels
   void set_kernel_mode(int m) { kernel_mode_ = m; }
   // scratch of the deterministic two-stage reductions, shared with driver-layer kernels that run on the same stream

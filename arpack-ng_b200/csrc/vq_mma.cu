@@ -37,16 +37,17 @@ constexpr int R = 128;             // rows per tile
 constexpr int RS = R + 4;          // shared-memory column stride of a tile (doubles)
 constexpr int NCW = 8;             // warps per consumer group
 constexpr int NG = 2;              // consumer groups
-constexpr int kThreads = (NG * NCW + 1) * 32;
+constexpr int QN = 4;              // a stage is filled and consumed in QN column groups: own mbarrier, own producer warp
+constexpr int kThreads = (NG * NCW + QN) * 32;
 constexpr int MAXK = 64;           // kin, kout <= 64
 constexpr int MAXST = 8;
-constexpr int QN = 4;              // a stage is filled and consumed in QN column groups, each with its own mbarrier
-constexpr uint32_t kBudget = 190 * 1024;
+constexpr uint32_t kSmemMax = 226 * 1024;   // dynamic shared memory of one CTA on sm_100 (227 KB) minus the static part
 
 struct VqMmaParams {
   int64_t n, ldv, ldo;
   int kin, kin4, kout, kp, qs;     // kin4 = kin rounded up to 4; kp = kout rounded up to 8; qs = kp + 4
   int nstages;
+  uint32_t q_elems;                // doubles reserved for Q in shared memory (kin4 * qs, rounded up)
   int qsteps;                      // k-steps (4 columns each) per column group of a stage
   uint32_t stage_elems;            // kin4 * RS
   const double* v;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* tiles = reinterpret_cast<double*>(smem);
   double* qsm = tiles + (size_t)p.nstages * p.stage_elems;               // [kin4][qs]
-  double* red = qsm + (size_t)MAXK * (MAXK + 4);                          // [NG*NCW]
+  double* red = qsm + p.q_elems;                                          // [NG*NCW]
   // full[s][q]: column group q of stage s has landed -- the consumers start their DMMAs on the first columns while
   // the later ones are still in flight, so that loading and computing overlap inside a stage as well as across stages
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NG * NCW + 8);
@@ -102,43 +103,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
   __syncthreads();
   const int64_t ntiles = (p.n + R - 1) / R;
   double nrm = 0.0;
-  if (warp == NG * NCW) {
-    // ---------------- producer warp ----------------
+  if (warp >= NG * NCW) {
+    // ---------------- producer warps: warp q feeds column group q of every stage ----------------
+    // (one thread issuing all 1 KB copies of a tile sustains ~20 GB/s per SM -- the copies are cheap but each is an
+    // instruction; QN issuers lift that ceiling above the SM's share of the HBM bandwidth)
+    const int q = warp - NG * NCW;
+    const int c0 = 4 * p.qsteps * q;
+    int c1 = c0 + 4 * p.qsteps;
+    c1 = c1 > p.kin ? p.kin : c1;
+    // Tile number `it` of this CTA lives in stage it % nstages, in phase (it / nstages) & 1 of that stage's barriers.
+    // Both sides derive stage and phase from `it`, so the ring depth need not be a multiple of the number of consumer
+    // groups: a group that meets a stage only every other time still waits for exactly the phase of ITS tile, and that
+    // phase cannot be overtaken (the next one needs this tile's consumers to release the stage first).
     int s = 0;
     uint32_t ph = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t row0 = t * R;
       const int rows = (int)((p.n - row0 < R) ? (p.n - row0) : R);
       double* dst = tiles + (size_t)s * p.stage_elems;
+      uint64_t* bar = full + s * QN + q;
       if (lane == 0) mbar_wait(empty + s, ph ^ 1u);
       __syncwarp();
-      if (rows == R) {
+      if (c1 <= c0) {
+        if (lane == 0) mbar_arrive(bar);   // nothing to load for this group (kin small): complete its phase all the same
+      } else if (rows == R) {
         if (lane == 0) {
-          for (int q = 0; q < QN; ++q) {
-            const int c0 = 4 * p.qsteps * q;
-            int c1 = c0 + 4 * p.qsteps;
-            c1 = c1 > p.kin ? p.kin : c1;
-            uint64_t* bar = full + s * QN + q;
-            if (c1 > c0) {
-              mbar_expect_tx(bar, (uint32_t)(c1 - c0) * (uint32_t)(R * sizeof(double)));
-              for (int c = c0; c < c1; ++c)
-                bulk_col(smem_u32(dst + (size_t)c * RS), p.v + row0 + (int64_t)c * p.ldv,
-                         (uint32_t)(R * sizeof(double)), bar);
-            } else {
-              mbar_arrive(bar);   // nothing to load for this group (kin small): complete its phase all the same
-            }
-          }
+          mbar_expect_tx(bar, (uint32_t)(c1 - c0) * (uint32_t)(R * sizeof(double)));
+          for (int c = c0; c < c1; ++c)
+            bulk_col(smem_u32(dst + (size_t)c * RS), p.v + row0 + (int64_t)c * p.ldv, (uint32_t)(R * sizeof(double)),
+                     bar);
         }
       } else {
         // last, partial tile: ordinary loads, zero fill (bulk copies need multiples of 16 bytes)
-        for (int i = lane; i < p.kin * R; i += 32) {
-          const int c = i / R, r = i - c * R;
+        for (int i = lane; i < (c1 - c0) * R; i += 32) {
+          const int c = c0 + i / R, r = i % R;
           dst[(size_t)c * RS + r] = (r < rows) ? p.v[row0 + r + (int64_t)c * p.ldv] : 0.0;
         }
         __threadfence_block();
         __syncwarp();
-        if (lane == 0)
-          for (int q = 0; q < QN; ++q) mbar_arrive(full + s * QN + q);
+        if (lane == 0) mbar_arrive(bar);
       }
       if (++s == p.nstages) { s = 0; ph ^= 1u; }
     }
@@ -146,9 +149,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
     // ---------------- consumers ----------------
     const int g = warp / NCW, gw = warp - g * NCW;
     const int qr = lane >> 2, qc = lane & 3;   // DMMA fragment coordinates
-    int s = g;
-    uint32_t ph = 0;
-    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x) {
+    const int nks = p.kin4 >> 2;
+    int it = g;   // CTA-local tile counter of my tiles: g, g + NG, ...
+    for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
+      const int s = it % p.nstages;
+      const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
       const int64_t row0 = t * R;
       const double* tile = tiles + (size_t)s * p.stage_elems;
       const double* ap = tile + (size_t)qc * RS + 16 * gw + qr;   // a[row = qr][k = qc] of k-step 0, m-block 0
@@ -158,26 +163,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
-      const int nks = p.kin4 >> 2;
-      int qnext = 0;   // next column group to wait for
-#pragma unroll 2
-      for (int ks = 0; ks < nks; ++ks) {
-        if (ks == qnext * p.qsteps) {
-          mbar_wait(full + s * QN + qnext, ph);
-          ++qnext;
-        }
-        const double a0 = ap[(size_t)(4 * ks) * RS], a1 = ap[(size_t)(4 * ks) * RS + 8];
+      for (int q = 0; q < QN; ++q) {
+        mbar_wait(full + s * QN + q, ph);
+        const int k0 = q * p.qsteps;
+        int k1 = k0 + p.qsteps;
+        k1 = k1 > nks ? nks : k1;
+#pragma unroll 4
+        for (int ks = k0; ks < k1; ++ks) {
+          const double a0 = ap[(size_t)(4 * ks) * RS], a1 = ap[(size_t)(4 * ks) * RS + 8];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          if (ks < (int)p.ksteps[nb]) {   // uniform: structural zeros of Q below the band are skipped
-            const double b = bp[(size_t)(4 * ks) * p.qs + 8 * nb];
-            dmma(acc[0][nb], a0, b);
-            dmma(acc[1][nb], a1, b);
+          for (int nb = 0; nb < NB; ++nb) {
+            if (ks < (int)p.ksteps[nb]) {   // uniform: structural zeros of Q below the band are skipped
+              const double b = bp[(size_t)(4 * ks) * p.qs + 8 * nb];
+              dmma(acc[0][nb], a0, b);
+              dmma(acc[1][nb], a1, b);
+            }
           }
         }
       }
-      // every column group must be observed in this phase, also those behind the last k-step (kin4/4 < QN*qsteps)
-      for (; qnext < QN; ++qnext) mbar_wait(full + s * QN + qnext, ph);
       // the tile is in registers now: hand the stage back before the stores
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
@@ -208,8 +211,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
           }
         }
       }
-      s += NG;
-      if (s >= p.nstages) { s -= p.nstages; ph ^= 1u; }
     }
     nrm = warp_sum(nrm);
     if (lane == 0) red[warp] = nrm;
@@ -225,17 +226,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
   finish_grid_reduce(p.partial, 1, 1, p.nrm2_out, p.ticket);
 }
 
-size_t aux_bytes() {
-  return sizeof(double) * ((size_t)MAXK * (MAXK + 4) + NG * NCW + 8) + sizeof(uint64_t) * (MAXST * QN + MAXST);
-}
+size_t aux_bytes() { return sizeof(double) * (NG * NCW + 8) + sizeof(uint64_t) * (MAXST * QN + MAXST); }
 
 template <int NB>
 cudaError_t launch(int grid, size_t smem, cudaStream_t s, const VqMmaParams& p) {
   static bool attr_set[kMaxDevices] = {};   // (function, device) attribute
   const int dev = current_device_slot();
   if (!attr_set[dev]) {
-    const cudaError_t e = cudaFuncSetAttribute(k_vq_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(kBudget + aux_bytes()));
+    const cudaError_t e = cudaFuncSetAttribute(k_vq_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
@@ -258,10 +256,14 @@ bool CudaVecOps<double>::vq_mma(int64_t n, int kin, int kout, const double* v, i
   p.qs = p.kp + 4;
   p.stage_elems = (uint32_t)p.kin4 * RS;
   p.qsteps = ((p.kin4 >> 2) + QN - 1) / QN;
-  int ns = (int)(kBudget / (p.stage_elems * sizeof(double)));
+  p.q_elems = ((uint32_t)(p.kin4 * p.qs) + 15u) & ~15u;
+  // small updates stay with the SIMT kernel (measured: kin*kout = 240 -> 5.5 vs 4.9 TB/s, 100 -> 4.7 vs 3.7)
+  static const int mma_min = getenv("AB200_VQ_MMA_MIN") ? atoi(getenv("AB200_VQ_MMA_MIN")) : 300;
+  if (kin * kout < mma_min) return false;
+  const size_t fixed = (size_t)p.q_elems * sizeof(double) + aux_bytes() + 128;
+  int ns = (int)((kSmemMax - fixed) / (p.stage_elems * sizeof(double)));
   ns = ns > MAXST ? MAXST : ns;
-  ns -= ns % NG;   // one consumer group per stage (see vecops_tma.cu, geometry())
-  if (ns < NG) return false;
+  if (ns < 2) return false;
   p.nstages = ns;
   p.v = v; p.q = qdev; p.out = out;
   p.with_resid = with_resid ? 1 : 0; p.beta_col = beta_col; p.sigma = sigma; p.beta = beta; p.resid = resid;
@@ -279,7 +281,7 @@ bool CudaVecOps<double>::vq_mma(int64_t n, int kin, int kout, const double* v, i
   const int grid = (int)(ntiles < num_sms_ ? ntiles : num_sms_);
   ensure_partial((size_t)grid);
   p.partial = partial_;
-  const size_t smem = (size_t)p.nstages * p.stage_elems * sizeof(double) + aux_bytes();
+  const size_t smem = (size_t)p.nstages * p.stage_elems * sizeof(double) + fixed;
   ProfScope ps(stream_, "vq_mma", (double)sizeof(double) * n * (kin + kout + (with_resid ? 2.0 : 0.0)));
   cudaError_t e;
   switch (nb) {
