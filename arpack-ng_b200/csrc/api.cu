@@ -196,6 +196,13 @@ Ctx<T>* make_ctx(const void* key, bool par, int comm_handle, int n, int ncv, T* 
   }
   Ctx<T>* raw = c.get();
   std::lock_guard<std::mutex> lk(g_mu);
+  // an unmodified ICB caller never calls ab200_release(): keep the table bounded by dropping finished solves
+  if (table<T>().size() >= 16) {
+    for (auto it = table<T>().begin(); it != table<T>().end();) {
+      if (it->first != key && it->second->finished) it = table<T>().erase(it);
+      else ++it;
+    }
+  }
   table<T>()[key] = std::move(c);
   return raw;
 }
@@ -353,7 +360,10 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
         c->ops->sync();
       }
     } else if (*ido == 99) {
-      g_last_counters = SYM ? c->sym->counters() : c->nonsym->counters();
+      {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_last_counters = SYM ? c->sym->counters() : c->nonsym->counters();
+      }
       // argument errors return before anything was built; every other exit leaves V/resid meaningful
       if (c->ops && c->n > 0 && (*info >= 0 || *info == -8 || *info == -9 || *info == -9999)) {
         if (c->resid_host) c->ops->download(resid, c->resid_d, (size_t)c->n);
@@ -368,6 +378,17 @@ void aupd_entry(bool par, int comm_handle, int* ido, const char* bmat, int n, co
     *info = kInfoDeviceError;
     *ido = 99;
   }
+}
+
+// *eupd is the last call of a solve (it destroys V, dseupd.f:730-746): a context that owns HBM mirrors of the
+// caller's host arrays -- n*(ncv+4) elements -- gives them back now instead of waiting for an ab200_release() that an
+// unmodified caller of the reference never makes.  (Device-resident callers own their arrays; nothing to free.)
+template <typename T>
+void drop_host_mirrors(Ctx<T>* c, const void* key) {
+  if (!(c->resid_host || c->v_host || c->workd_host || c->z_mirror != nullptr)) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = table<T>().find(key);
+  if (it != table<T>().end() && it->second.get() == c) table<T>().erase(it);
 }
 
 template <typename T>
@@ -425,6 +446,7 @@ void seupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const 
       if (c->v_host) c->ops->download2d(v, (size_t)ldv, c->v_d, (size_t)c->ldv_d, (size_t)n, (size_t)ncv);
     }
     c->ops->sync();
+    drop_host_mirrors<T>(c, workl);
   } catch (const std::exception& e) {
     report<T>("[ds]seupd_c", e);
     *info = kInfoDeviceError;
@@ -454,6 +476,7 @@ void neupd_entry(bool par, int comm_handle, int rvec, const char* howmny, const 
       if (c->v_host) c->ops->download2d(v, (size_t)ldv, c->v_d, (size_t)c->ldv_d, (size_t)n, (size_t)ncv);
     }
     c->ops->sync();
+    drop_host_mirrors<T>(c, workl);
   } catch (const std::exception& e) {
     report<T>("[ds]neupd_c", e);
     *info = kInfoDeviceError;

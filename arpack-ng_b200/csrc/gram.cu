@@ -95,7 +95,20 @@ __global__ void k_permute(long long nnz, const int* __restrict__ perm, const int
 
 // y (+)= A x, LPR lanes per row (power of two); entries of a row are summed lane-strided, then an xor tree: a fixed
 // order, so the product is bit-reproducible.  The vector gathered at random is pinned in L2 by the launch attribute.
-template <int LPR>
+// gather flavours of x (AB200_GRAM_LD): 0 = plain load, 1 = read-only path (ld.global.nc), 2 = read-only and not
+// allocated in L1 (every gathered sector is used once per SM: keeping it in L1 only evicts the streams)
+template <int LD>
+__device__ __forceinline__ double gather(const double* p) {
+  if (LD == 1) return __ldg(p);
+  if (LD == 2) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+  }
+  return *p;
+}
+
+template <int LPR, int LD>
 __global__ void __launch_bounds__(256) k_spmv_rows(int nrows, const int* __restrict__ rowptr,
                                                    const int* __restrict__ col, const double* __restrict__ val,
                                                    const double* __restrict__ x, double* __restrict__ y, int acc) {
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(256) k_spmv_rows(int nrows, const int* __restr
   for (long long row = sub; row < nrows; row += nsub) {
     const int p0 = rowptr[row], p1 = rowptr[row + 1];
     double a = 0.0;
-    for (int p = p0 + lane; p < p1; p += LPR) a += __ldcs(val + p) * x[__ldcs(col + p)];
+    for (int p = p0 + lane; p < p1; p += LPR) a += __ldcs(val + p) * gather<LD>(x + __ldcs(col + p));
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o, LPR);
     if (lane == 0) y[row] = acc ? y[row] + a : a;
@@ -121,6 +134,7 @@ L2Window& l2window() {
   if (!w.ready) {
     w.ready = true;
     static const bool off = getenv("AB200_L2_WINDOW") && std::strcmp(getenv("AB200_L2_WINDOW"), "0") == 0;
+    (void)off;
     int dev = 0, max_persist = 0, max_win = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
@@ -133,11 +147,19 @@ L2Window& l2window() {
   return w;
 }
 
+// Measured on the full-size config-5 shards (B200, 2.5 M x 5 M, 40 M entries; tools/gram_probe.py): the product is
+// bound by the L2 -> SM sector traffic of the 8-byte gathers (ncu: DRAM bytes = 1.00 x algorithmic, every gathered
+// sector delivers 8 of its 32 bytes, lts throughput 55 %, l1tex 65 %), not by DRAM.  Few lanes per row win (A x, 16
+// entries per row: 8 lanes 2.7 TB/s, 16 lanes 2.2, 32 lanes 1.5, 2 lanes 2.0; A^T w, ~8 per row: 4 lanes 2.5, 8 lanes
+// 1.9), gathers that bypass L1 help a little, and the L2 window pays for x (re-used by every shard) but not for w.
 int launch_rows(cudaStream_t s, int nrows, long long nnz, const int* rowptr, const int* col, const double* val,
-                const double* x, size_t x_bytes, double* y, int acc, const char* name) {
+                const double* x, size_t x_bytes, double* y, int acc, const char* name, bool pin_x) {
   if (nrows <= 0) return 0;
   const double avg = (double)nnz / nrows;
-  const int lpr = avg <= 3.0 ? 2 : avg <= 6.0 ? 4 : avg <= 12.0 ? 8 : avg <= 24.0 ? 16 : 32;
+  int lpr = avg <= 12.0 ? 4 : avg <= 24.0 ? 8 : avg <= 48.0 ? 16 : 32;
+  static const int lpr_env = getenv("AB200_GRAM_LPR") ? atoi(getenv("AB200_GRAM_LPR")) : 0;   // tuning knobs
+  static const int ld_env = getenv("AB200_GRAM_LD") ? atoi(getenv("AB200_GRAM_LD")) : 2;
+  if (lpr_env == 1 || lpr_env == 2 || lpr_env == 4 || lpr_env == 8 || lpr_env == 16 || lpr_env == 32) lpr = lpr_env;
   long long g = ((long long)nrows * lpr + 255) / 256;
   const long long cap = 148LL * 32;
   g = g > cap ? cap : (g < 1 ? 1 : g);
@@ -148,7 +170,7 @@ int launch_rows(cudaStream_t s, int nrows, long long nnz, const int* rowptr, con
   cudaLaunchAttribute attr[1];
   int nattr = 0;
   const size_t win = l2window().max_window;
-  if (win > 0 && x_bytes > 0) {
+  if (win > 0 && x_bytes > 0 && pin_x) {
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
     attr[0].val.accessPolicyWindow.base_ptr = const_cast<double*>(x);
     attr[0].val.accessPolicyWindow.num_bytes = x_bytes < win ? x_bytes : win;
@@ -161,13 +183,19 @@ int launch_rows(cudaStream_t s, int nrows, long long nnz, const int* rowptr, con
   cfg.numAttrs = nattr;
   ProfScope ps(s, name, (double)nnz * 12.0 + (nrows + 1) * 4.0 + (double)x_bytes + (acc ? 16.0 : 8.0) * nrows);
   cudaError_t e;
+#define AB200_ROWS(LPR_)                                                                                      \
+  (ld_env == 2   ? cudaLaunchKernelEx(&cfg, k_spmv_rows<LPR_, 2>, nrows, rowptr, col, val, x, y, acc)          \
+   : ld_env == 1 ? cudaLaunchKernelEx(&cfg, k_spmv_rows<LPR_, 1>, nrows, rowptr, col, val, x, y, acc)          \
+                 : cudaLaunchKernelEx(&cfg, k_spmv_rows<LPR_, 0>, nrows, rowptr, col, val, x, y, acc))
   switch (lpr) {
-    case 2: e = cudaLaunchKernelEx(&cfg, k_spmv_rows<2>, nrows, rowptr, col, val, x, y, acc); break;
-    case 4: e = cudaLaunchKernelEx(&cfg, k_spmv_rows<4>, nrows, rowptr, col, val, x, y, acc); break;
-    case 8: e = cudaLaunchKernelEx(&cfg, k_spmv_rows<8>, nrows, rowptr, col, val, x, y, acc); break;
-    case 16: e = cudaLaunchKernelEx(&cfg, k_spmv_rows<16>, nrows, rowptr, col, val, x, y, acc); break;
-    default: e = cudaLaunchKernelEx(&cfg, k_spmv_rows<32>, nrows, rowptr, col, val, x, y, acc); break;
+    case 1: e = AB200_ROWS(1); break;
+    case 2: e = AB200_ROWS(2); break;
+    case 4: e = AB200_ROWS(4); break;
+    case 8: e = AB200_ROWS(8); break;
+    case 16: e = AB200_ROWS(16); break;
+    default: e = AB200_ROWS(32); break;
   }
+#undef AB200_ROWS
   launch_stats().kernels++;
   return e == cudaSuccess ? 0 : -1;
 }
@@ -226,10 +254,10 @@ int gram_apply(int handle, const double* x_loc, double* z_loc) {
     for (size_t i = 0; i < G->shards.size(); ++i) {
       const Shard& sh = G->shards[i];
       if (launch_rows(s, sh.nrows, sh.nnz, sh.rowptr, sh.col, sh.val, x, sizeof(double) * G->ncols, G->w, 0,
-                      "gram_Ax") != 0)
+                      "gram_Ax", true) != 0)
         return -3;
       if (launch_rows(s, G->ncols, sh.nnz, sh.t_rowptr, sh.t_col, sh.t_val, G->w, sizeof(double) * sh.nrows, z,
-                      i > 0 ? 1 : 0, "gram_ATw") != 0)
+                      i > 0 ? 1 : 0, "gram_ATw", false) != 0)
         return -4;
     }
     if (c && G->nranks > 1) nccl_reducescatter_sum(c, G->zfull, z_loc, per_rank, true, s);
