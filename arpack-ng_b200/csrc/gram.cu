@@ -151,7 +151,9 @@ L2Window& l2window() {
 // bound by the L2 -> SM sector traffic of the 8-byte gathers (ncu: DRAM bytes = 1.00 x algorithmic, every gathered
 // sector delivers 8 of its 32 bytes, lts throughput 55 %, l1tex 65 %), not by DRAM.  Few lanes per row win (A x, 16
 // entries per row: 8 lanes 2.7 TB/s, 16 lanes 2.2, 32 lanes 1.5, 2 lanes 2.0; A^T w, ~8 per row: 4 lanes 2.5, 8 lanes
-// 1.9), gathers that bypass L1 help a little, and the L2 window pays for x (re-used by every shard) but not for w.
+// 1.9) and gathers that bypass L1 help a little -- but only together with the L2 access-policy window on the gathered
+// vector: once the device has a persisting set-aside, un-windowed gathers of the other product lose half their rate
+// (1.2 TB/s inside a solve), so both products pin their vector (2.6 / 2.2 TB/s).
 int launch_rows(cudaStream_t s, int nrows, long long nnz, const int* rowptr, const int* col, const double* val,
                 const double* x, size_t x_bytes, double* y, int acc, const char* name, bool pin_x) {
   if (nrows <= 0) return 0;
@@ -257,7 +259,7 @@ int gram_apply(int handle, const double* x_loc, double* z_loc) {
                       "gram_Ax", true) != 0)
         return -3;
       if (launch_rows(s, G->ncols, sh.nnz, sh.t_rowptr, sh.t_col, sh.t_val, G->w, sizeof(double) * sh.nrows, z,
-                      i > 0 ? 1 : 0, "gram_ATw", false) != 0)
+                      i > 0 ? 1 : 0, "gram_ATw", true) != 0)
         return -4;
     }
     if (c && G->nranks > 1) nccl_reducescatter_sum(c, G->zfull, z_loc, per_rank, true, s);

@@ -81,16 +81,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
   double* red = qsm + p.q_elems;                                          // [NG*NCW]
   // full[s][q]: column group q of stage s has landed -- the consumers start their DMMAs on the first columns while
   // the later ones are still in flight, so that loading and computing overlap inside a stage as well as across stages
+  // Every (stage, consumer group) pair has its OWN set of full barriers: with a ring depth that is not a multiple of
+  // NG a stage serves the groups alternately, and a group that met a barrier only every other phase could take the
+  // completion of phase k-2 for that of phase k (mbarrier waits see one parity bit).  With a barrier per pair each
+  // group observes every phase of the barriers it waits on; tile number `it` of the CTA uses stage it % nstages,
+  // group it % NG and phase it / lcm(nstages, NG) of that pair.  The empty barrier of a stage is shared: its only
+  // waiter, the producer, sees all of its phases.
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NG * NCW + 8);
-  uint64_t* empty = full + MAXST * QN;
+  uint64_t* empty = full + MAXST * NG * QN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < p.nstages; ++s) {
-      for (int q = 0; q < QN; ++q) mbar_init(full + s * QN + q, 1);
+      for (int q = 0; q < NG * QN; ++q) mbar_init(full + s * NG * QN + q, 1);
       mbar_init(empty + s, NCW);
     }
     mbar_fence_init();
   }
+  const int period = (p.nstages % NG == 0) ? p.nstages : p.nstages * NG;   // lcm(nstages, NG) for NG = 2
   // Q^T-free layout: qsm[k][c], zero-padded to kin4 x kp
   for (int i = tid; i < p.kin4 * p.qs; i += kThreads) {
     const int k = i / p.qs, c = i - k * p.qs;
@@ -111,17 +118,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
     const int c0 = 4 * p.qsteps * q;
     int c1 = c0 + 4 * p.qsteps;
     c1 = c1 > p.kin ? p.kin : c1;
-    // Tile number `it` of this CTA lives in stage it % nstages, in phase (it / nstages) & 1 of that stage's barriers.
-    // Both sides derive stage and phase from `it`, so the ring depth need not be a multiple of the number of consumer
-    // groups: a group that meets a stage only every other time still waits for exactly the phase of ITS tile, and that
-    // phase cannot be overtaken (the next one needs this tile's consumers to release the stage first).
-    int s = 0;
-    uint32_t ph = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int s = 0, it = 0;
+    uint32_t ph = 0;   // phase of the stage's empty barrier
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int64_t row0 = t * R;
       const int rows = (int)((p.n - row0 < R) ? (p.n - row0) : R);
       double* dst = tiles + (size_t)s * p.stage_elems;
-      uint64_t* bar = full + s * QN + q;
+      uint64_t* bar = full + (s * NG + it % NG) * QN + q;
       if (lane == 0) mbar_wait(empty + s, ph ^ 1u);
       __syncwarp();
       if (c1 <= c0) {
@@ -153,7 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
     int it = g;   // CTA-local tile counter of my tiles: g, g + NG, ...
     for (int64_t t = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; t < ntiles; t += (int64_t)NG * gridDim.x, it += NG) {
       const int s = it % p.nstages;
-      const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+      const uint32_t ph = (uint32_t)(it / period) & 1u;
+      uint64_t* fullg = full + (s * NG + g) * QN;
       const int64_t row0 = t * R;
       const double* tile = tiles + (size_t)s * p.stage_elems;
       const double* ap = tile + (size_t)qc * RS + 16 * gw + qr;   // a[row = qr][k = qc] of k-step 0, m-block 0
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
       for (int q = 0; q < QN; ++q) {
-        mbar_wait(full + s * QN + q, ph);
+        mbar_wait(fullg + q, ph);
         const int k0 = q * p.qsteps;
         int k1 = k0 + p.qsteps;
         k1 = k1 > nks ? nks : k1;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vq_mma(const VqMmaParams p) {
   finish_grid_reduce(p.partial, 1, 1, p.nrm2_out, p.ticket);
 }
 
-size_t aux_bytes() { return sizeof(double) * (NG * NCW + 8) + sizeof(uint64_t) * (MAXST * QN + MAXST); }
+size_t aux_bytes() { return sizeof(double) * (NG * NCW + 8) + sizeof(uint64_t) * (MAXST * NG * QN + MAXST); }
 
 template <int NB>
 cudaError_t launch(int grid, size_t smem, cudaStream_t s, const VqMmaParams& p) {

@@ -17,10 +17,16 @@ KEEP = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "l1tex__m_xbar2l1tex_read_sectors_mem_global_op_tma_ld.sum"]
+        "l1tex__m_xbar2l1tex_read_sectors_mem_global_op_tma_ld.sum",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 # profiler names used by the library's CUDA-event profiler (bench.py roofline keys) per kernel-name fragment
 NAMES = [("k_orth", None), ("k_csr_spmv_bulk", "csr_spmv"), ("k_csr_spmv_stream", "csr_spmv"), ("k_csr_spmv", "csr_spmv"),
-         ("k_vq_tma", "vq_tma"), ("k_start_step", "start_step")]
+         ("k_vq_tma", "vq_tma"), ("k_vq_mma", "vq_mma"), ("k_start_step", "start_step"), ("k_spmv_rows", "gram_spmv")]
 
 
 def main():
