@@ -9,15 +9,19 @@ exits with info = 1) on the 2-D 5-point Laplacian nx x nx (n = nx^2, CSR FP64), 
 tol=1e-10, start vector = the hashed vector of SURVEY.md §8(d).  value = OP*x count (iparam(9)) / time.
 
   value : device-resident path -- A, resid, V, workd live in HBM, the ido=+-1 hand-off passes device pointers to
-          the CSR SpMV kernel; timed with CUDA events on the library's stream, max over ranks.
-  e2e   : the same solve through dsaupd_c with everything the caller owns in HOST (pinned) memory -- the CSR matrix,
-          resid, V, workd.  The caller registers its host matrix (ab200_register_csr_op_f64, one call before ido = 0);
-          A and resid are uploaded, the solve runs in one dsaupd_c call, V and resid come back at ido = 99, all inside
-          the timed region.  e2e_rci_handoff is the same with the unmodified reverse-communication loop: every hand-off
-          crosses PCIe (library: D2H x, H2D y; OP: H2D x, SpMV, D2H y).  Byte counts are those of the copies issued.
-  roofline : the dominant kernel of the timed region (by accumulated CUDA-event time), achieved = algorithmic bytes
-          charged per launch / event time, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline : the oracle port (oracle/libref_arpack.so + OpenBLAS, all host threads) on a bounded sample.
+          the CSR SpMV kernel (the library enqueues a whole sweep without waiting for the GPU); timed with CUDA events
+          on the library's stream, max over ranks, WITHOUT the per-kernel profiler.
+  e2e   : the SAME reverse-communication loop with the caller's resid, V, workd in HOST (pinned) memory: every hand-off
+          crosses PCIe (library: D2H x, H2D y; the caller's GPU OP: H2D x, SpMV, D2H y), V and resid come back at
+          ido = 99 -- all inside the timed region.  e2e_registered_host_csr: the caller also owns the CSR matrix on the
+          host and registers it (ab200_register_csr_op_f64): A and resid up, one dsaupd_c call, V and resid down.
+  value_mxiter1 : the GPU on the restart budget of the reference arm (mxiter = 1).
+  roofline : the dominant kernel by accumulated CUDA-event time of ONE extra solve after the timed region (same
+          launches), achieved = algorithmic bytes charged per launch / event time, against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline : the oracle port (oracle/libref_arpack.so + OpenBLAS, all host threads) on a bounded sample;
+  fullsize_parity : that run's projected matrix, Ritz values, bounds and counts against a GPU run of the same budget.
+  config3 : north_star's target (3-D 7-point Laplacian 512^3, nev 20, ncv 64, z-slabs over the ranks): steps/s on a
+          fixed restart budget, per-step HBM fraction, kernel share; time to solution from 4 GPUs up.
 """
 import argparse
 import ctypes as C
