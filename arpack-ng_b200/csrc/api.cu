@@ -17,6 +17,7 @@
 // and prints the reason on stderr.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -42,9 +43,10 @@ namespace {
 
 constexpr int kInfoDeviceError = -9990;
 
-cudaStream_t g_stream = 0;
-int g_kernel_mode = 0;
-int g_compat = 0;  // ab200_set_compat(): bit 0 = maintain workd(ipntr(3)) in mode 1
+// process-wide settings: read at ido = 0 of a solve, written by the ab200_set_* calls (possibly from another thread)
+std::atomic<cudaStream_t> g_stream{nullptr};
+std::atomic<int> g_kernel_mode{0};
+std::atomic<int> g_compat{0};  // ab200_set_compat(): bit 0 = maintain workd(ipntr(3)) in mode 1
 std::mutex g_mu;
 
 // COMMON /debug/ (debug.h) and the counters of COMMON /timing/ (stat.h) of the last solve
@@ -168,9 +170,9 @@ Ctx<T>* make_ctx(const void* key, bool par, int comm_handle, int n, int ncv, T* 
     comm = comm_from_handle(comm_handle);
     if (!comm) throw CudaError("p*aupd_c: comm is not a handle returned by ab200_comm_create()");
   }
-  c->ops = ops_pool<T>().take(g_stream, comm);
+  c->ops = ops_pool<T>().take(g_stream.load(), comm);
   c->comm_ptr = comm;
-  c->ops->set_kernel_mode(g_kernel_mode);
+  c->ops->set_kernel_mode(g_kernel_mode.load());
   c->par = par;
   c->n = n;
   c->ncv = ncv;
@@ -657,7 +659,7 @@ void stat_c(a_int* nopx, a_int* nbx, a_int* nrorth, a_int* nitref, a_int* nrstrt
 
 // ---- extensions --------------------------------------------------------------------------------
 void ab200_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
-void* ab200_get_stream(void) { return (void*)g_stream; }
+void* ab200_get_stream(void) { return (void*)g_stream.load(); }
 void ab200_set_kernel_mode(int mode) { g_kernel_mode = mode; }
 void ab200_set_compat(int flags) { g_compat = flags; }
 void ab200_release(const void* workl) {
@@ -674,6 +676,7 @@ void ab200_release_all(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   table<double>().clear();
   table<float>().clear();
+  ab200_forget_csr_cache();
   ops_pool<double>().clear();
   ops_pool<float>().clear();
   registered_ops<double>().clear();  // descriptors hold the caller's pointers: none may outlive this call
@@ -768,8 +771,8 @@ int ab200_debug_orth_f64(long long n, int j, const double* v, long long ldv, con
                          double* out_host) {
   try {
     require_device();
-    CudaVecOps<double> ops(g_stream, nullptr);
-    ops.set_kernel_mode(g_kernel_mode);
+    CudaVecOps<double> ops(g_stream.load(), nullptr);
+    ops.set_kernel_mode(g_kernel_mode.load());
     const int seg = j + 2;
     double* mb = ops.mailbox((size_t)3 * seg);
     ops.orth_step(n, j, v, ldv, w, resid, mb, mb + seg, mb + 2 * seg);
@@ -791,8 +794,8 @@ int ab200_debug_vq_f64(long long n, int kin, int kout, double* v, long long ldv,
                        double beta, int beta_col, double* resid, double* nrm2_host) {
   try {
     require_device();
-    CudaVecOps<double> ops(g_stream, nullptr);
-    ops.set_kernel_mode(g_kernel_mode);
+    CudaVecOps<double> ops(g_stream.load(), nullptr);
+    ops.set_kernel_mode(g_kernel_mode.load());
     double* mb = ops.mailbox(8);
     ops.vq_update(n, kin, kout, v, ldv, q_host, kin, true, sigma, beta, beta_col, resid, mb);
     ops.fetch(nrm2_host, mb, 1);
@@ -808,8 +811,8 @@ int ab200_debug_vq_f64(long long n, int kin, int kout, double* v, long long ldv,
 int ab200_kernel_probe_f64(long long n, int j, int ncv, int iters, int what, int kout) {
   try {
     require_device();
-    CudaVecOps<double> ops(g_stream, nullptr);
-    ops.set_kernel_mode(g_kernel_mode);
+    CudaVecOps<double> ops(g_stream.load(), nullptr);
+    ops.set_kernel_mode(g_kernel_mode.load());
     const int64_t ldv = (n + 1) & ~1LL;
     double* v = ops.alloc((size_t)ldv * ncv);
     double* w = ops.alloc((size_t)n);

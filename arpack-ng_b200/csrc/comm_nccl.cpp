@@ -94,10 +94,10 @@ void check(ncclResult_t r, const char* what) {
 
 // in-kernel waits give up (trap -> a CUDA error on the host) after this many SM cycles; 0 = wait for ever.
 // Ranks of a reverse-communication solver legitimately drift apart between calls (a slow user OP, I/O on one rank),
-// so the default is long: 600 s.  AB200_P2P_TIMEOUT_S overrides it (0 = unbounded, like an MPI collective).
+// so the default is long: 300 s.  AB200_P2P_TIMEOUT_S overrides it (0 = unbounded, like an MPI collective).
 long long wait_budget_cycles() {
   static const long long v = [] {
-    double s = 600.0;
+    double s = 300.0;
     if (const char* e = getenv("AB200_P2P_TIMEOUT_S")) s = atof(e);
     return s <= 0.0 ? 0LL : (long long)(s * 1.9e9);
   }();

@@ -606,13 +606,18 @@ int launch_spmv(int nrows, const int* rowptr, const int* col, const T* val, cons
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// nnz of a CSR matrix whose rowptr lives on the device, cached per rowptr address
+// nnz of a CSR matrix whose rowptr lives on the device, cached per (rowptr address, rows).  The value only steers the
+// choice of kernel and its tile shape (every kernel reads the true row bounds on the device and handles any row
+// length), so a stale entry -- the arrays were freed and others of the same size allocated at the same address --
+// costs performance at worst, never correctness.  ab200_release_all() forgets the cache.
+struct NnzEntry { const int* ptr; int rows; long long nnz; };
+NnzEntry g_nnz_cache[8] = {};
 long long nnz_of(int nrows, const int* rowptr) {
-  struct Entry { const int* ptr; int rows; long long nnz; };
-  static Entry cache[8] = {};
+  typedef NnzEntry Entry;
+  Entry* cache = g_nnz_cache;
   static int next = 0;
-  for (const Entry& e : cache)
-    if (e.ptr == rowptr && e.rows == nrows) return e.nnz;
+  for (int i = 0; i < 8; ++i)
+    if (cache[i].ptr == rowptr && cache[i].rows == nrows) return cache[i].nnz;
   int h = 0;
   if (cudaMemcpyAsync(&h, rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, cur_stream()) != cudaSuccess) return 0;
   cudaStreamSynchronize(cur_stream());
@@ -840,6 +845,9 @@ using namespace ab200;
 extern "C" {
 
 
+void ab200_forget_csr_cache(void) {
+  for (auto& e : g_nnz_cache) e = NnzEntry{nullptr, 0, 0};
+}
 void ab200_set_spmv_variant(int variant) { spmv_variant() = (variant >= 0 && variant <= 4) ? variant : 0; }
 
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y) {

@@ -22,16 +22,18 @@ template <typename T>
 __device__ __forceinline__ bool gate_eval_block(const StepGate<T>& g, T& inv) {
   __shared__ T s_inv;
   __shared__ int s_ok;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {   // the first warp decides (every kernel that uses the gate has at least one full warp)
+    const int lane = (int)threadIdx.x;
     const T wn = sqrt(g.A[g.prev_j]);
     T rn = sqrt(g.B[g.prev_j]);
     bool ok = true;
-    if (!(rn > T(0.717f) * wn)) {  // the DGKS pass ran (dsaitr.f:656)
+    if (!(rn > T(0.717f) * wn)) {  // the DGKS pass ran (dsaitr.f:656); uniform across the warp
       T c0;
       if (g.peer.nranks > 0) {
-        for (int p = 0; p < g.peer.nranks; ++p) peer_wait_rank(g.peer, p);
+        if (lane < g.peer.nranks) peer_wait_rank(g.peer, lane);   // one lane per rank: the waits overlap
+        __syncwarp();
         c0 = peer_sum<T>(g.peer, 0);
-        if (blockIdx.x == 0 && g.c_log != nullptr) g.c_log[0] = c0;
+        if (blockIdx.x == 0 && lane == 0 && g.c_log != nullptr) g.c_log[0] = c0;
       } else {
         c0 = g.C[0];
       }
@@ -40,8 +42,10 @@ __device__ __forceinline__ bool gate_eval_block(const StepGate<T>& g, T& inv) {
       else ok = false;
     }
     if (!(rn >= g.tiny) || !(rn > T(0))) ok = false;
-    s_inv = T(1) / rn;
-    s_ok = ok ? 1 : 0;
+    if (lane == 0) {
+      s_inv = T(1) / rn;
+      s_ok = ok ? 1 : 0;
+    }
   }
   __syncthreads();
   inv = s_inv;

@@ -54,7 +54,7 @@ __device__ __forceinline__ void peer_wait_rank(const PeerReduce& pr, int src) {
   unsigned int spins = 0;
   while (peer_load_acquire(f) < pr.seq) {
     // a peer that never arrives must not hang the GPU for ever unless the user asked for that: trap after the
-    // configured time (default 600 s, AB200_P2P_TIMEOUT_S; 0 = wait like MPI would)
+    // configured time (default 300 s, AB200_P2P_TIMEOUT_S; 0 = wait like MPI would)
     if (pr.timeout_cycles > 0 && ((++spins & 0x3FFu) == 0)) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;

@@ -202,6 +202,8 @@ void ab200_set_kernel_mode(int mode);
 void ab200_set_compat(int flags);
 void ab200_release(const void* workl);
 void ab200_release_all(void);
+/* forget the per-address nnz cache of ab200_csr_spmv_f64/f32 (also done by ab200_release_all) */
+void ab200_forget_csr_cache(void);
 /* out4 = {kernels launched, all-reduces issued, TMA-path launches, generic-path launches} since load */
 void ab200_launch_stats(unsigned long long* out4);
 /* blocking device->host mailbox reads since load: one per Lanczos/Arnoldi step in the synchronous mode, one per sweep
@@ -269,7 +271,8 @@ void* ab200_comm_halo_buffer(int handle, long long halo_lo, long long halo_hi, i
  * does these products with Eigen on the CPU).  All pointers are DEVICE pointers unless named *_host. ---- */
 /* y = A x, CSR with int32 indices (K3 of SURVEY.md §2.3) */
 int ab200_csr_spmv_f64(int nrows, const int* rowptr, const int* col, const double* val, const double* x, double* y);
-/* SpMV kernel for short-row matrices: 0 = CSR-bulk (cp.async.bulk ring, default), 1 = CSR-stream, 2 = row per sub-warp */
+/* SpMV kernel for short-row matrices: 0 = CSR-bulk (cp.async.bulk ring, row-owner consumers; default), 1 = CSR-stream,
+ * 2 = row per sub-warp, 4 = CSR-bulk with parked products (the round-1 consumers); all return the same bits */
 void ab200_set_spmv_variant(int variant);
 int ab200_csr_spmv_f32(int nrows, const int* rowptr, const int* col, const float* val, const float* x, float* y);
 /* as above with host vectors: H2D(x), SpMV, D2H(y) -- the OP of an unmodified host RCI loop */
