@@ -212,13 +212,6 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
                                                              unsigned int* ticket, const StepGate<T> gate,
                                                              const T* stop) {
   constexpr int CAP = ROWS * EPT;  // entries per ring slot, alignment pad included
-  if (FUSED) {
-    if (stopped(stop)) return;
-    if (gate.stop != nullptr && !gate_eval_block(gate, xs)) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
-      return;
-    }
-  }
   using Stage = SpmvBulkStage<T, ROWS, CAP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
@@ -228,12 +221,22 @@ __global__ void __launch_bounds__(ROWS + 32) k_csr_spmv_bulk(int nrows, const in
   const int tid = threadIdx.x;
   const int nblk = (nrows + ROWS - 1) / ROWS;
   const int gstep = (int)gridDim.x;
+  // prologue without global-memory accesses: may overlap the tail of the previous kernel (tma::launch_pdl)
+  tma::pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       tma::mbar_init(&full[i], 1);
       tma::mbar_init(&empty[i], ROWS / 32);
     }
     tma::mbar_fence_init();
+  }
+  tma::pdl_wait();
+  if (FUSED) {
+    if (stopped(stop)) return;
+    if (gate.stop != nullptr && !gate_eval_block(gate, xs)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) *gate.stop = gate.stop_code;
+      return;
+    }
   }
   __syncthreads();
   const int nnz4 = __ldg(rowptr + nrows) & ~3;
@@ -496,10 +499,11 @@ int launch_spmv_bulk_cfg(cudaStream_t s, int ctas_per_sm, int nrows, long long n
   long long g = (long long)sms * ctas_per_sm;
   if (g > nblk) g = nblk;
   (void)nnz;
-  kern<<<(int)g, ROWS + 32, smem, s>>>(nrows, rowptr, col, val, x, y, nloc, xh, xs, vj_out, partial, dots_out, ticket,
-                                       gate, stop);
+  const cudaError_t e = tma::launch_pdl(kern, (int)g, ROWS + 32, smem, s, nrows, rowptr, col, val, x, y, nloc, xh, xs,
+                                        vj_out, partial, dots_out, ticket, gate, stop);
   launch_stats().kernels++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  if (e != cudaSuccess) cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1;
 }
 
 // the bulk kernel needs 16-byte aligned CSR arrays (cp.async.bulk) and the true nnz

@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "gate.cuh"
+#include "tma_common.cuh"
 #include "vecops_cuda.cuh"
 
 namespace ab200 {
@@ -350,6 +351,8 @@ __global__ void k_scal(int64_t n, T alpha, T* x) {
 template <typename T>
 __global__ void k_start_step(int64_t n, T inv, const T* __restrict__ resid, T* __restrict__ vj,
                              T* __restrict__ outx, T* bx, bool bx_from_resid, const T* stop) {
+  tma::pdl_trigger();
+  tma::pdl_wait();
   if (stopped(stop)) return;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     const T t = resid[r] * inv;
@@ -363,6 +366,8 @@ __global__ void k_start_step(int64_t n, T inv, const T* __restrict__ resid, T* _
 template <typename T>
 __global__ void k_start_step_gated(int64_t n, const StepGate<T> g, const T* __restrict__ resid, T* __restrict__ vj,
                                    T* __restrict__ outx, T* bx) {
+  tma::pdl_trigger();
+  tma::pdl_wait();
   if (stopped(g.stop)) return;
   T inv;
   if (!gate_eval_block(g, inv)) {
@@ -768,8 +773,9 @@ void CudaVecOps<T>::start_step(int64_t n, T inv, const T* resid, T* vj, T* outx,
   resolve_pending();
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? (from_resid ? 4.0 : 5.0) : 3.0));
-  k_start_step<T><<<grid, 256, 0, stream_>>>(n, inv, resid, vj, outx, bx, from_resid, stop_);
-  AB200_LAUNCHED();
+  AB200_CUDA_CHECK(tma::launch_pdl(k_start_step<T>, grid, 256, 0, stream_, n, inv, resid, vj, outx, bx, from_resid,
+                                   (const T*)stop_));
+  launch_stats().kernels++;
 }
 template <typename T>
 void CudaVecOps<T>::start_step_gated(int64_t n, const StepGate<T>& g0, const T* resid, T* vj, T* outx, T* bx) {
@@ -777,8 +783,8 @@ void CudaVecOps<T>::start_step_gated(int64_t n, const StepGate<T>& g0, const T* 
   attach_pending(g);  // multi-GPU: the gate finishes the reduction of ||r'||^2 itself
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms_ * 8);
   ProfScope ps(stream_, "start_step", (double)sizeof(T) * n * (bx ? 4.0 : 3.0));
-  k_start_step_gated<T><<<grid, 256, 0, stream_>>>(n, g, resid, vj, outx, bx);
-  AB200_LAUNCHED();
+  AB200_CUDA_CHECK(tma::launch_pdl(k_start_step_gated<T>, grid, 256, 0, stream_, n, g, resid, vj, outx, bx));
+  launch_stats().kernels++;
 }
 template <typename T>
 void CudaVecOps<T>::ger(int64_t n, int k, const T* resid, const T* w_host, T* z, int64_t ldz) {

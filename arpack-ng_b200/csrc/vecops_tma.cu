@@ -92,12 +92,25 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreadsTma, 1)
 k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  if (stopped(p.stop)) return;
+  pdl_trigger();
   T* tiles = reinterpret_cast<T*>(smem);
   unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
   T* ps = reinterpret_cast<T*>(aux);                     // [NG groups][2 buffers][2 halves][R]
   T* cs = ps + NG * 4 * R;                               // [MAXB*CB] coefficients
   T* gsum = cs + MAXB * CB;                              // [MAXB*CB + 8] partials of consumer group 1
+  {
+    // prologue that touches no global memory: may overlap the tail of the previous kernel (launch_pdl)
+    uint64_t* full0 = reinterpret_cast<uint64_t*>(gsum + MAXB * CB + 8);
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < p.nstages; ++s) {
+        mbar_init(full0 + s, 1);
+        mbar_init(full0 + MAXST + s, NCW);
+      }
+      mbar_fence_init();
+    }
+  }
+  pdl_wait();
+  if (stopped(p.stop)) return;
   const bool sub = MODE != DOTS && p.sub.nranks > 0;
   T tail = T(0);
   if (sub) tail = fused_coefs(p, cs);
@@ -112,13 +125,6 @@ k_orth(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
   uint64_t* full = reinterpret_cast<uint64_t*>(gsum + MAXB * CB + 8);
   uint64_t* empty = full + MAXST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < p.nstages; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, NCW);
-    }
-    mbar_fence_init();
-  }
   if (MODE != DOTS && !sub)
     for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
   __syncthreads();
@@ -282,11 +288,24 @@ template <typename T, bool SPEC, int KB>
 __global__ void __launch_bounds__(kThreadsTma, 1)
 k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, const OrthParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  if (stopped(p.stop)) return;
+  pdl_trigger();
   T* tiles = reinterpret_cast<T*>(smem);
   unsigned char* aux = smem + (size_t)p.nstages * p.stage_bytes;
   T* wsum = reinterpret_cast<T*>(aux);                   // [NG*NCW warps][MAXB*CB columns]  (== NG*4*R elements)
   T* cs = wsum + NG * 4 * R;                             // [MAXB*CB] coefficients
+  {
+    // prologue that touches no global memory: may overlap the tail of the previous kernel (launch_pdl)
+    uint64_t* full0 = reinterpret_cast<uint64_t*>(cs + MAXB * CB + MAXB * CB + 8);
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < p.nstages; ++s) {
+        mbar_init(full0 + s, 1);
+        mbar_init(full0 + MAXST + s, NCW);
+      }
+      mbar_fence_init();
+    }
+  }
+  pdl_wait();
+  if (stopped(p.stop)) return;
   const bool sub = p.sub.nranks > 0;
   T tail = T(0);
   if (sub) tail = fused_coefs(p, cs);
@@ -302,13 +321,6 @@ k_upd(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
   uint64_t* full = reinterpret_cast<uint64_t*>(wnrm + MAXB * CB + 8);
   uint64_t* empty = full + MAXST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < p.nstages; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, NCW);
-    }
-    mbar_fence_init();
-  }
   if (!sub)
     for (int k = tid; k < MAXB * CB; k += kThreadsTma) cs[k] = (k < p.j) ? p.coef[k] : T(0);
   __syncthreads();
@@ -637,10 +649,9 @@ bool launch_orth(cudaStream_t stream, int num_sms, const T* v, int64_t ldv, Orth
   const int64_t ntiles = (p.n + R - 1) / R;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   ProfScope ps(stream, name, bytes);
-  k_orth<T, MODE><<<grid, kThreadsTma, smem, stream>>>(map, xmap, p);
+  AB200_CUDA_CHECK(launch_pdl(k_orth<T, MODE>, grid, kThreadsTma, smem, stream, map, xmap, p));
   launch_stats().kernels++;
   launch_stats().fast_path++;
-  AB200_CUDA_CHECK(cudaGetLastError());
   return true;
 }
 
@@ -657,8 +668,7 @@ bool launch_upd_kb(cudaStream_t stream, int grid, size_t smem, const CUtensorMap
     }
     attr_set[dev] = true;
   }
-  k_upd<T, SPEC, KB><<<grid, kThreadsTma, smem, stream>>>(map, xmap, p);
-  return true;
+  return launch_pdl(k_upd<T, SPEC, KB>, grid, kThreadsTma, smem, stream, map, xmap, p) == cudaSuccess;
 }
 
 // UPD / UPD_SPEC through k_upd (rows per lane); AB200_UPD=old keeps the k_orth form for A/B measurements
