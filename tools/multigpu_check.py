@@ -11,6 +11,7 @@ the same eigenvalues to 1e-10 relative (the bar of BASELINE.json's north_star).
   3. the same solve with the operator registered (ab200_register_csr_halo_op_f64): no hand-off, same path
   4. pdnaupd_c/pdneupd_c: 2-D convection-diffusion (dndrv1.f:453-470, rho = 10), row blocks, nev 4 ncv 20 'LM'
   5. pznaupd_c/pzneupd_c: icb_parpack_c.c:104-190 -- diag((i+1)(1+i)), rvec = 0
+  7. pssaupd_c (FP32): 2-D Laplacian by y-slabs, eigenvalues to 1e-4 (north_star's FP32 bar)
   6. BASELINE config 5 at test size: SVD through pdsaupd_c on A^T A, A 20k x 5k with 16 nnz/row ROW-SHARDED over the
      ranks (all-gather x, local A and A^T products, reduce-scatter; EXAMPLES/SVD/dsvd.f:342-343), hand-off and registered
 
@@ -188,6 +189,35 @@ for reg in (False, True):
            g.info == 0 and g.ierr == 0 and counts_of(g) == counts_of(o) and rel <= 1e-10 and (g.nsteps == 0) == reg,
            f"counts gpu={counts_of(g)} oracle={counts_of(o)} rel sigma diff={rel:.1e} sigma_max={sg.max():.6f}")
 G5.close()
+
+# ---- 7. pssaupd_c: the single-precision twin (fused reductions on 4-byte values), 2-D Laplacian by y-slabs ----
+nx7, ny7 = 40, 8 * world
+y0, nyl = ab.slab_partition(ny7, world, rank)
+n7 = nyl * nx7
+cnts7 = [ab.slab_partition(ny7, world, r)[1] * nx7 for r in range(world)]
+from problems import laplace2d  # noqa: E402
+S7 = laplace2d(nx7, ny7).tocsr().astype(np.float32)
+S7_loc = S7[y0 * nx7:(y0 + nyl) * nx7, :]
+r7 = np.random.default_rng(5).uniform(-1, 1, nx7 * ny7).astype(np.float32)[y0 * nx7:(y0 + nyl) * nx7]
+xg7 = torch.zeros(nx7 * ny7, dtype=torch.float32, device="cuda")
+ch7 = list(torch.split(xg7, cnts7))
+S7d = ab.CsrOperator.from_scipy(S7_loc.astype(np.float64))
+S7d.val = S7d.val.to(torch.float32)
+
+
+def op7(x, yv, *_):
+    ch7[rank].copy_(x)
+    for r in range(world):
+        dist.broadcast(ch7[r], src=r)
+    S7d(xg7, yv)
+
+
+g = ab.solve(op7, n7, 4, 16, "LA", tol=1e-5, mxiter=3000, resid=r7, comm=comm, dtype=np.float32)
+o = oracle().solve(lambda x: (S7_loc @ host_allgather(x, cnts7)).astype(np.float32), n7, 4, 16, "LA", tol=1e-5,
+                   mxiter=3000, resid=r7, c_abi_tol=True, dtype=np.float32)
+rel = np.abs(g.d - o.d).max() / np.abs(o.d).max()
+report("pssaupd_c laplace2d (FP32)", g.info == 0 and g.ierr == 0 and g.nconv == o.nconv and rel <= 1e-4,
+       f"counts gpu={counts_of(g)} oracle={counts_of(o)} rel eig diff={rel:.1e}")
 
 st = ab.launch_stats()
 print(f"[rank {rank}] launches={st} reductions over: {path}", flush=True)
