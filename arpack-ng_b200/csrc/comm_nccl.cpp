@@ -174,9 +174,12 @@ __global__ void __launch_bounds__(kPeerMaxCount) k_p2p_allreduce(T* mb, int coun
 
 // end of a fused reduction whose consumer is not a kernel of ours (the host is about to read the value): add the
 // ranks' slots into log[0..count).  With a predicate the reduction only exists when the DGKS pass ran (dsaitr.f:656).
+// A sweep whose stop flag is up produced nothing after the step that tripped it (the producers exited at entry, the
+// mailbox slots of those steps still hold values of an earlier sweep): nothing to wait for then.
 template <typename T>
 __global__ void __launch_bounds__(kPeerMaxCount) k_peer_finalize(PeerReduce pr, int count, T* log, const T* pred_w2,
-                                                                 const T* pred_r2) {
+                                                                 const T* pred_r2, const T* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile T*>(stop) != T(0)) return;
   if (pred_w2 != nullptr) {
     const T wn = sqrt(*pred_w2), rn = sqrt(*pred_r2);
     if (rn > T(0.717f) * wn) return;
@@ -273,14 +276,14 @@ bool nccl_peer_reduce_begin(NcclComm* c, int kind, PeerReduce* out) {
   return true;
 }
 void nccl_peer_reduce_finalize(NcclComm* c, const PeerReduce& pr, int count, void* log, const void* pred_w2,
-                               const void* pred_r2, bool is_double, cudaStream_t s) {
+                               const void* pred_r2, const void* stop, bool is_double, cudaStream_t s) {
   (void)c;
   if (is_double)
     k_peer_finalize<double><<<1, kPeerMaxCount, 0, s>>>(pr, count, (double*)log, (const double*)pred_w2,
-                                                        (const double*)pred_r2);
+                                                        (const double*)pred_r2, (const double*)stop);
   else
     k_peer_finalize<float><<<1, kPeerMaxCount, 0, s>>>(pr, count, (float*)log, (const float*)pred_w2,
-                                                       (const float*)pred_r2);
+                                                       (const float*)pred_r2, (const float*)stop);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw CudaError(std::string("peer-reduce finalize launch failed: ") + cudaGetErrorString(e));
   launch_stats().kernels++;

@@ -623,7 +623,8 @@ template <typename T>
 void CudaVecOps<T>::resolve_pending() {
   if (!has_pending_) return;
   has_pending_ = false;
-  nccl_peer_reduce_finalize(comm_, pending_, 1, pending_log_, pending_w2_, pending_r2_, sizeof(T) == 8, stream_);
+  nccl_peer_reduce_finalize(comm_, pending_, 1, pending_log_, pending_w2_, pending_r2_, pending_stop_, sizeof(T) == 8,
+                            stream_);
 }
 template <typename T>
 void CudaVecOps<T>::fetch(T* host_dst, const T* mb, size_t count) {

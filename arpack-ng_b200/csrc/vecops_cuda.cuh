@@ -31,7 +31,7 @@ int nccl_nranks(const NcclComm* c);
 // reductions fused into the kernels on both sides (peer memory; comm_nccl.cpp, peer.cuh)
 bool nccl_peer_reduce_begin(NcclComm* c, int kind, PeerReduce* out);
 void nccl_peer_reduce_finalize(NcclComm* c, const PeerReduce& pr, int count, void* log, const void* pred_w2,
-                               const void* pred_r2, bool is_double, cudaStream_t s);
+                               const void* pred_r2, const void* stop, bool is_double, cudaStream_t s);
 
 // process-wide launch statistics (bench.py reports gpu_launches from here)
 struct LaunchStats {
@@ -178,6 +178,7 @@ class CudaVecOps final : public VecOps<T> {
   T* pending_log_ = nullptr;
   const T* pending_w2_ = nullptr;
   const T* pending_r2_ = nullptr;
+  const T* pending_stop_ = nullptr;   // the sweep's stop flag at the time the reduction was started
   // Fused reductions are a protocol between the ranks' kernels: either every rank runs the TMA-tiled kernels for this
   // solve's V (alignment, leading dimension -- rank-local properties) or nobody fuses.  Agreed once per (V, ldv).
   const void* agreed_v_ = nullptr;

@@ -785,6 +785,7 @@ bool CudaVecOps<T>::orth_step_tma(int64_t n, int j, const T* v, int64_t ldv, con
     pending_log_ = mbC;
     pending_w2_ = mbA + j;
     pending_r2_ = mbB + j;
+    pending_stop_ = stop_;
   } else {
     allreduce_sum(mbC, 1);
   }

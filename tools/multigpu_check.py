@@ -11,6 +11,7 @@ the same eigenvalues to 1e-10 relative (the bar of BASELINE.json's north_star).
   3. the same solve with the operator registered (ab200_register_csr_halo_op_f64): no hand-off, same path
   4. pdnaupd_c/pdneupd_c: 2-D convection-diffusion (dndrv1.f:453-470, rho = 10), row blocks, nev 4 ncv 20 'LM'
   5. pznaupd_c/pzneupd_c: icb_parpack_c.c:104-190 -- diag((i+1)(1+i)), rvec = 0
+  8. pdsaupd_c with a start vector inside an invariant subspace: the device-resident sweep is cut short on every rank
   7. pssaupd_c (FP32): 2-D Laplacian by y-slabs, eigenvalues to 1e-4 (north_star's FP32 bar)
   6. BASELINE config 5 at test size: SVD through pdsaupd_c on A^T A, A 20k x 5k with 16 nnz/row ROW-SHARDED over the
      ranks (all-gather x, local A and A^T products, reduce-scatter; EXAMPLES/SVD/dsvd.f:342-343), hand-off and registered
@@ -218,6 +219,20 @@ o = oracle().solve(lambda x: (S7_loc @ host_allgather(x, cnts7)).astype(np.float
 rel = np.abs(g.d - o.d).max() / np.abs(o.d).max()
 report("pssaupd_c laplace2d (FP32)", g.info == 0 and g.ierr == 0 and g.nconv == o.nconv and rel <= 1e-4,
        f"counts gpu={counts_of(g)} oracle={counts_of(o)} rel eig diff={rel:.1e}")
+
+# ---- 8. a sweep cut short on every rank: start vector inside a 3-dimensional invariant subspace of diag(1..N) ----
+# rnorm collapses in mid-sweep, the gated start of the next step trips the stop flag, the remaining kernels (and their
+# fused reductions) of the batch are no-ops on all ranks, and pdsaitr's restart (pdgetv0, per-rank seeds) takes over
+r8 = np.zeros(N)
+r8[[3, N // 2 + 1, N - 7]] = [1.0, -2.0, 0.5]
+r8 = r8[first:first + cnt]
+L.ab200_reset_seed()
+g = ab.solve(lambda x, y, *_: torch.mul(diag, x, out=y), cnt, 4, 12, "LM", tol=1e-10, mxiter=2000, resid=r8, comm=comm)
+o = oracle().solve(lambda x: diag_h * x, cnt, 4, 12, "LM", tol=1e-10, mxiter=2000, resid=r8, c_abi_tol=True)
+rel = np.abs(np.sort(g.d) - np.sort(o.d)).max() / np.abs(o.d).max()
+report("pdsaupd_c breakdown + restart in mid-sweep", g.info == o.info and g.nconv == o.nconv and rel <= 1e-8 and
+       o.stats["nrstrt"] > 0, f"info={g.info}/{o.info} nconv={g.nconv}/{o.nconv} oracle restarts of the factorisation="
+       f"{o.stats['nrstrt']} rel eig diff={rel:.1e}")
 
 st = ab.launch_stats()
 print(f"[rank {rank}] launches={st} reductions over: {path}", flush=True)
