@@ -119,14 +119,189 @@ def test_restart_files(files):
     assert "restart KO" in err or "bad restart" in err
 
 
-def test_max_iterations_and_rejected_options(files):
+def test_max_iterations_and_bad_options(files):
     d = files[0]
     _, err = run(d, "--A", "As.mtx", "--nbEV", 3, "--nbCV", 7, "--mag", "SA", "--maxIt", 1, "--noCheck")
     assert "maximum number of iterations taken" in err           # info = 1 is reported, not fatal (arpackSolver.hpp:791)
-    for bad, msg in ((["--cpxPb"], "not built"), (["--dense", "true"], "not built"), (["--slv", "LU"], "not built"),
-                     (["--slvItrPC", "ILU"], "not built"), (["--mag", "XX"], "bad --mag"), (["--nbEV"], "need argument"),
-                     (["--A", "missing.mtx"], "read A KO")):
+    for bad, msg in ((["--dense", "maybe"], "bad --dense"), (["--dense", "true"], "does not support iterative solvers"),
+                     (["--genPb", "--slv", "XX"], "bad --slv"), (["--genPb", "--slvItrPC", "SSOR"], "bad --slvItrPC"),
+                     (["--mag", "XX"], "bad --mag"), (["--nbEV"], "need argument"), (["--A", "missing.mtx"], "read A KO")):
         _, err = run(d, *(["--A", "As.mtx"] if "--A" not in bad else []), *bad, expect=1)
         assert msg in err
+    # the reference's parser skips what it does not know (arpackmm.sh passes a bare "LA"); so does this one, loudly
+    out, err = run(d, "--A", "As.mtx", "LA", "--nbEV", 2, "--nbCV", 12, "--maxIt", 500)
+    assert "unknown option LA ignored" in err and found(out)[1] == 2
     out, _ = run(d, "--help")
-    assert "--nbEV" in out and "--restart" in out
+    assert "--nbEV" in out and "--restart" in out and "--slvItrPC" in out and "--dense" in out
+
+
+def write_mtx_complex(path, A, base=0):
+    """the reference's complex files (Az.mtx, Bz.mtx): 'i j (re, im)' entries, no banner needed"""
+    A = sp.coo_matrix(A)
+    with open(path, "w") as f:
+        f.write("% complex coordinate file\n\n")
+        f.write(f"{A.shape[0]} {A.shape[1]}\n\n")
+        for r, c, v in zip(A.row, A.col, A.data):
+            f.write(f"{r + base}  {c + base}  ({float(v.real)!r}, {float(v.imag)!r})\n")
+
+
+# (solver options, extra options, also run mode 3) -- a cut of arpackmm.sh's --slv x --dense x --simplePrec sweep
+GEN_CASES = [
+    (["--slv", "BiCG", "--slvItrPC", "ILU#1.e-06#2"], [], True),
+    (["--slv", "CG", "--slvItrPC", "ILU"], [], False),          # "ILU" alone: drop tolerance 1, i.e. almost Jacobi
+    (["--slv", "BiCG"], ["--simplePrec"], False),
+    (["--slv", "LU"], [], True),
+    (["--slv", "LU"], ["--simplePrec"], False),
+    (["--slv", "QR", "--slvDrtPivot", "1.e-06"], [], False),
+    (["--slv", "LLT"], [], True),
+    (["--slv", "LDLT", "--slvDrtScale", "1."], [], True),
+    (["--slv", "LU", "--dense", "true"], [], False),
+    (["--slv", "QR", "--dense", "false"], ["--simplePrec"], False),
+    (["--slv", "LLT", "--dense", "true"], [], False),
+    (["--slv", "LDLT", "--dense", "false"], [], True),
+]
+
+
+@pytest.mark.parametrize("slv,prec,mode3", GEN_CASES, ids=lambda s: "-".join(x.strip("-") for x in s) if isinstance(s, list) else "")
+def test_generalised_every_solver(files, slv, prec, mode3):
+    """arpackmm.sh's --slv sweep on a symmetric generalised problem: mode 2 (B^-1 A, B SPD) and mode 3 (shift-invert
+    around 1; A - B is indefinite there, which LLT must refuse and LDLT must survive by falling back)."""
+    d, As, _, Bm = files
+    gev = np.sort(sl.eigh(As.toarray(), Bm.toarray(), eigvals_only=True))
+    itr = ["--slvItrTol", "1.e-7" if prec else "1.e-12", "--slvItrMaxIt", 2000] if slv[1] in ("BiCG", "CG") else []
+    tol = 2e-3 if prec else 1e-6
+    out, _ = run(d, "--A", "As.mtx", "--genPb", "--nbEV", 3, "--nbCV", 20, "--mag", "LM", "--maxIt", 500, "--verbose", 1,
+                 *slv, *itr, *prec)
+    assert found(out)[0] == 2
+    assert np.abs(np.sort([v.real for v in values(out)]) - gev[-3:]).max() < tol * gev[-1]
+    assert re.search(r"inner solver %s: \d+ solves" % slv[1], out)
+    if not mode3:
+        return
+    args = ["--A", "As.mtx", "--genPb", "--nbEV", 3, "--nbCV", 20, "--mag", "LM", "--shiftReal", 1.0, "--maxIt", 500,
+            "--verbose", 1, *slv, *itr, *prec]
+    if slv[1] == "LLT":
+        _, err = run(d, *args, expect=1)
+        assert "not positive definite" in err
+        return
+    out, err = run(d, *args)
+    assert found(out)[0] == 3
+    if slv[1] == "LDLT":
+        assert "Warning: LDLT" in err
+    near = gev[np.argsort(np.abs(gev - 1.0))[:3]]
+    assert np.abs(np.sort([v.real for v in values(out)]) - np.sort(near)).max() < tol
+
+
+def test_cholesky_offset_and_scale(files):
+    """--slvDrtOffset / --slvDrtScale change the diagonal the sparse Cholesky factorises (Eigen's setShift), so the inner
+    solves belong to a modified B.  Arnoldi (dn*upd) does not need OP to be self-adjoint in the B inner product: its Ritz
+    values are eigenvalues of Bmod^-1 A."""
+    d, As, _, Bm = files
+    Bmod = Bm.toarray().copy()
+    Bmod[np.diag_indices_from(Bmod)] = 0.5 + 2.0 * np.diag(Bmod)
+    out, _ = run(d, "--nonSymPb", "--A", "As.mtx", "--genPb", "--nbEV", 2, "--nbCV", 16, "--maxIt", 500, "--verbose", 1,
+                 "--slv", "LLT", "--slvDrtOffset", 0.5, "--slvDrtScale", 2.0, "--noCheck")
+    ev = np.linalg.eigvals(np.linalg.solve(Bmod, As.toarray()))
+    got = values(out)
+    assert len(got) >= 2
+    for v in got:
+        assert np.abs(ev - v).min() < 1e-5 * np.abs(ev).max()
+
+
+@pytest.mark.parametrize("slv", [["--slv", "LU"], ["--slv", "QR", "--dense", "false"]], ids=["LU", "denseQR"])
+def test_nonsymmetric_generalised_shift_invert(files, slv):
+    d, _, An, Bm = files
+    ev = sl.eigvals(An.toarray(), Bm.toarray())
+    out, _ = run(d, "--nonSymPb", "--A", "An.mtx", "--genPb", "--nbEV", 4, "--nbCV", 24, "--shiftReal", 2.0, "--maxIt",
+                 1000, "--verbose", 1, *slv)
+    mode, nb, _ = found(out)
+    assert mode == 3 and nb >= 4
+    near = ev[np.argsort(np.abs(ev - 2.0))[:4]]
+    got = values(out)
+    for v in near:
+        assert min(abs(v - g) for g in got) < 1e-6
+
+
+@pytest.fixture(scope="module")
+def zfiles(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mmz")
+    n = 48
+    k = np.arange(n)
+    Az = sp.diags([(-1.0 - 0.1j) * np.ones(n - 1), (2.0 + 0.05 * k) + 0.3j * np.cos(k), (-1.0 + 0.3j) * np.ones(n - 1)],
+                  [-1, 0, 1]).tocsr()
+    Bz = sp.diags([np.ones(n - 1) / 6, 4 * np.ones(n) / 6, np.ones(n - 1) / 6], [-1, 0, 1]).astype(complex).tocsr()
+    write_mtx_complex(d / "Az.mtx", Az, base=0)
+    write_mtx_complex(d / "Bz.mtx", Bz, base=1)
+    return d, Az, Bz
+
+
+@pytest.mark.parametrize("extra", [[], ["--simplePrec"], ["--mag", "LI"], ["--shiftReal", "3.0"],
+                                   ["--shiftReal", "3.0", "--shiftImag", "1.0"]],
+                         ids=lambda e: "-".join(x.strip("-") for x in e) or "LM")
+def test_complex_standard(zfiles, extra):
+    """--cpxPb: zn[ae]upd / cn[ae]upd on a complex non-Hermitian matrix (arpackmm.sh's third eigPb)."""
+    d, Az, _ = zfiles
+    out, _ = run(d, "--nonSymPb", "--cpxPb", "--A", "Az.mtx", "--nbEV", 3, "--nbCV", 20, "--maxIt", 1000, "--verbose", 1, *extra)
+    mode, nb, _ = found(out)
+    assert mode == 1 and nb == 3
+    assert ("backTransform yes" in out) == (extra == ["--shiftReal", "3.0"])   # only a purely real shift is applied
+    ev = np.linalg.eigvals(Az.toarray())
+    tol = 2e-3 if "--simplePrec" in extra else 1e-6
+    got = values(out)
+    for v in got:
+        assert np.abs(ev - v).min() < tol
+    if extra == ["--shiftReal", "3.0"]:
+        want = ev[np.argsort(-np.abs(ev - 3.0))[:3]]
+        for v in want:
+            assert min(abs(v - g) for g in got) < tol
+
+
+@pytest.mark.parametrize("slv", [["--slv", "BiCG", "--slvItrPC", "ILU#1.e-08#4", "--slvItrTol", "1.e-12", "--slvItrMaxIt", 500],
+                                 ["--slv", "LU"], ["--slv", "QR", "--dense", "false"]], ids=["BiCG-ILU", "LU", "denseQR"])
+def test_complex_generalised(zfiles, slv):
+    d, Az, Bz = zfiles
+    ev = sl.eigvals(Az.toarray(), Bz.toarray())
+    # mode 2: OP = B^-1 A, largest magnitude
+    out, _ = run(d, "--nonSymPb", "--cpxPb", "--A", "Az.mtx", "--B", "Bz.mtx", "--genPb", "--nbEV", 3, "--nbCV", 20,
+                 "--maxIt", 1000, "--verbose", 1, *slv)
+    assert found(out)[0] == 2
+    want = ev[np.argsort(-np.abs(ev))[:3]]
+    got = values(out)
+    for v in want:
+        assert min(abs(v - g) for g in got) < 1e-6 * np.abs(ev).max()
+    if "--dense" in slv:
+        return
+    # mode 3 with a complex shift: the eigenvalues nearest sigma
+    sigma = 6.0 + 1.0j
+    out, _ = run(d, "--nonSymPb", "--cpxPb", "--A", "Az.mtx", "--B", "Bz.mtx", "--genPb", "--nbEV", 3, "--nbCV", 20,
+                 "--shiftReal", sigma.real, "--shiftImag", sigma.imag, "--maxIt", 1000, "--verbose", 1, *slv)
+    assert found(out)[0] == 3
+    want = ev[np.argsort(np.abs(ev - sigma))[:3]]
+    got = values(out)
+    for v in want:
+        assert min(abs(v - g) for g in got) < 1e-6
+
+
+def test_complex_llt_and_restart(zfiles):
+    d, Az, Bz = zfiles
+    ev = sl.eigvals(Az.toarray(), Bz.toarray())
+    args = ["--nonSymPb", "--cpxPb", "--A", "Az.mtx", "--B", "Bz.mtx", "--genPb", "--nbEV", 3, "--nbCV", 20, "--maxIt", 1000,
+            "--verbose", 1, "--slv", "LLT"]
+    out1, _ = run(d, *args)    # B is Hermitian positive definite: complex sparse Cholesky
+    want = ev[np.argsort(-np.abs(ev))[:3]]
+    for v in want:
+        assert min(abs(v - g) for g in values(out1)) < 1e-6 * np.abs(ev).max()
+    first = open(d / "arpackSolver.resid.out").read().split("\n")
+    assert int(first[0]) == Az.shape[0] and first[1].startswith("(")        # complex dumps: "(re,im)" lines
+    out2, _ = run(d, *args, "--restart")
+    assert "restart OK" in out2
+    for v in want:
+        assert min(abs(v - g) for g in values(out2)) < 1e-6 * np.abs(ev).max()
+
+
+def test_stat_lines(files):
+    """the STAT block of arpackmm.cpp:1046-1060 (stat_c counters of the solve that just ran)"""
+    d = files[0]
+    out, _ = run(d, "--A", "As.mtx", "--nbEV", 3, "--nbCV", 20, "--mag", "LA", "--maxIt", 500)
+    m = re.search(r"STAT: total number of user OP\*x operation\s+(\d+)", out)
+    assert m and int(m.group(1)) > 20
+    assert re.search(r"STAT: total number of reorthogonalization steps taken\s+\d+", out)
