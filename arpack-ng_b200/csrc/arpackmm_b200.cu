@@ -366,7 +366,7 @@ __global__ void k_dot_partial(int n, const S* x, const S* y, double* partial) {
 // x = T^-1 b for a triangular CSR matrix T = (strict part) + diagonal, level by level inside ONE thread block: the
 // rows of a level only need rows of earlier levels.  dinv = inverse diagonal, or null for a unit diagonal.
 template <typename S>
-__global__ void k_sptrsv_levels(int nlevels, const int* __restrict__ level_ptr, const int* __restrict__ level_rows,
+__global__ void __launch_bounds__(1024) k_sptrsv_levels(int nlevels, const int* __restrict__ level_ptr, const int* __restrict__ level_rows,
                                 const int* __restrict__ rp, const int* __restrict__ ci, const S* __restrict__ v,
                                 const S* __restrict__ dinv, const S* __restrict__ b, S* x) {
   for (int l = 0; l < nlevels; ++l) {
@@ -454,6 +454,7 @@ struct DevMat {
     if (dense) {
       const int g = std::min(1184, std::max(1, (n + 7) / 8));
       k_dense_rows<S><<<g, 256, 0, stream>>>(n, val, x, y);
+      CK(cudaGetLastError());
     } else if constexpr (std::is_same<S, double>::value) {
       if (ab200_csr_spmv_f64(n, rowptr, col, val, x, y) != 0) { std::cerr << "Error: SpMV KO" << std::endl; std::exit(1); }
     } else if constexpr (std::is_same<S, float>::value) {
@@ -461,6 +462,7 @@ struct DevMat {
     } else {
       const int g = std::min(1184, std::max(1, (n + 7) / 8));
       k_csr_rows<S><<<g, 256, 0, stream>>>(n, rowptr, col, val, x, y);
+      CK(cudaGetLastError());
     }
   }
 };
@@ -628,6 +630,7 @@ struct Preconditioner {
     } else {
       k_sptrsv_levels<S><<<1, 1024, 0, stream>>>(L.nlevels, L.level_ptr, L.level_rows, L.rp, L.ci, L.v, (const S*)nullptr, r, tmp);
       k_sptrsv_levels<S><<<1, 1024, 0, stream>>>(U.nlevels, U.level_ptr, U.level_rows, U.rp, U.ci, U.v, dinv, tmp, z);
+      CK(cudaGetLastError());
     }
   }
 };
